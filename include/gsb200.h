@@ -1,0 +1,231 @@
+/*
+ * gsb200.h -- C ABI of libgsb200.so: the B200-native (sm_100a) replacement for the hot path of
+ * gsgen3d/gsgen's `_gs` PyTorch extension (gs/src/bindings.cpp:5-82, gs/src/render.h:3-155).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (tensor.data_ptr()) unless the name starts with `h_`;
+ *     fp32 / int32 / uint8 exactly as the reference's CHECK_DC_FLOAT / CHECK_DC_INT contracts
+ *     (gs/src/include/common.h:46-54); tensors are contiguous.
+ *   - the caller owns all outputs (reference render.h: every op mutates pre-allocated tensors and
+ *     returns void); gradient buffers of the reference-compatible ops are ACCUMULATED into (the
+ *     caller zero-fills them, gs/renderer.py:1223-1226).
+ *   - every entry point returns GSB200_OK or an error code and never exits the process (the
+ *     reference printf+exit(-1)s on CUDA errors, common.h:56-72); the message is available from
+ *     gsb200_last_error().  The Python shim raises RuntimeError like TORCH_CHECK does.
+ *   - `stream` is a cudaStream_t (the reference launches on the legacy default stream,
+ *     render.cu:505 only for SH); all work is enqueued on it, nothing synchronises unless stated.
+ *   - tile_size must be 16 (every reference config, conf/base.yaml:132); other values return
+ *     GSB200_ERR_UNSUPPORTED.
+ */
+#ifndef GSB200_H_
+#define GSB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB200_OK 0
+#define GSB200_ERR_INVALID 1     /* contract violation (TORCH_CHECK in the reference)            */
+#define GSB200_ERR_CUDA 2        /* CUDA runtime / launch error                                   */
+#define GSB200_ERR_UNSUPPORTED 3 /* e.g. tile_size != 16, SH C outside 1..4 (render.cu:507-545)   */
+#define GSB200_ERR_MISMATCH 4    /* duplicate count != gaussian_ids size (aabb_culling.h:228)      */
+
+typedef struct gsb200_ctx gsb200_ctx; /* per-device scratch arena + saved state of one view       */
+typedef void* gsb200_stream;           /* cudaStream_t                                              */
+
+const char* gsb200_last_error(void);
+int gsb200_version(void);
+int gsb200_ctx_create(int device, gsb200_ctx** out);
+int gsb200_ctx_destroy(gsb200_ctx* ctx);
+
+/* ================================================================================================
+ * Part 1 -- one entry point per hot-path function of the reference `_gs` module, same argument
+ * order and meaning (shape arguments the reference reads from tensor sizes are explicit here).
+ * ============================================================================================== */
+
+/* _gs.culling_gaussian_bsphere  render.h:3-5, render.cu:16-44, culling.h:11-34.
+ * mask[i] = sphere(mean_i, thresh*max(svec_i)) intersects the 6-plane frustum.  qvec is unused
+ * (as in the reference) and may be NULL.  mask is a bool tensor (1 byte / element). */
+int gsb200_culling_gaussian_bsphere(const float* mean, const float* qvec, const float* svec,
+                                    const float* normal, const float* pts, uint8_t* mask, uint32_t N,
+                                    float thresh, gsb200_stream stream);
+
+/* _gs.tile_culling_aabb_start_end  render.h:65-68, render.cu:381-398, aabb_culling.h:192-260.
+ * Duplicates each Gaussian over its tile rectangle with key (tile<<32)|float_bits(depth), sorts
+ * (cub::DeviceRadixSort), writes gaussian_ids[D] (sorted) and start/end[T] (-1 for empty tiles).
+ * Synchronises once to verify the duplicate count against D (the reference's host assert). */
+int gsb200_tile_culling_aabb_start_end(gsb200_ctx* ctx, const int32_t* aabb_topleft,
+                                       const int32_t* aabb_bottomright, int32_t* gaussian_ids,
+                                       int32_t* start, int32_t* end, const float* depth, uint32_t N,
+                                       uint32_t N_with_dub, uint32_t n_tiles_h, uint32_t n_tiles_w,
+                                       gsb200_stream stream);
+
+/* _gs.tile_based_vol_rendering_start_end_with_T  render.h:151-155, vol_render.h:994-1079, and
+ * _gs.tile_based_vol_rendering_start_end (render.h:70-76) when T == NULL.
+ * out[H,W,3] / T[H,W] must be pre-initialised (zeros / ones): empty tiles are left untouched. */
+int gsb200_tile_based_vol_rendering_start_end_with_T(
+    gsb200_ctx* ctx, const float* mean, const float* cov, const float* color, const float* alpha,
+    const int32_t* start, const int32_t* end, const int32_t* gaussian_ids, float* out,
+    const float* topleft, uint32_t N, uint32_t N_with_dub, uint32_t tile_size, uint32_t n_tiles_h,
+    uint32_t n_tiles_w, float pixel_size_x, float pixel_size_y, uint32_t H, uint32_t W, float thresh,
+    float* T, gsb200_stream stream);
+
+/* _gs.tile_based_vol_rendering_backward_start_end  render.h:78-84, vol_render.h:866-992.
+ * `out` is the saved forward output INCLUDING the background term (gs/renderer.py:1182,1190). */
+int gsb200_tile_based_vol_rendering_backward_start_end(
+    gsb200_ctx* ctx, const float* mean, const float* cov, const float* color, const float* alpha,
+    const int32_t* start, const int32_t* end, const int32_t* gaussian_ids, const float* out,
+    float* grad_mean, float* grad_cov, float* grad_color, float* grad_alpha, const float* grad_out,
+    const float* topleft, uint32_t N, uint32_t N_with_dub, uint32_t tile_size, uint32_t n_tiles_h,
+    uint32_t n_tiles_w, float pixel_size_x, float pixel_size_y, uint32_t H, uint32_t W, float thresh,
+    gsb200_stream stream);
+
+/* _gs.tile_based_vol_rendering_scalar  render.h:134-141, vol_render_scalar.h:47-102.
+ * scalar may hold more than N entries (A.9-16); only indices < N are read. */
+int gsb200_tile_based_vol_rendering_scalar(
+    gsb200_ctx* ctx, const float* mean, const float* cov, const float* scalar, const float* alpha,
+    const int32_t* start, const int32_t* end, const int32_t* gaussian_ids, float* out,
+    const float* topleft, uint32_t N, uint32_t N_with_dub, uint32_t tile_size, uint32_t n_tiles_h,
+    uint32_t n_tiles_w, float pixel_size_x, float pixel_size_y, uint32_t H, uint32_t W, float thresh,
+    float* T, gsb200_stream stream);
+
+/* _gs.tile_based_vol_rendering_scalar_backward  render.h:143-149, vol_render_scalar.h:148-234. */
+int gsb200_tile_based_vol_rendering_scalar_backward(
+    gsb200_ctx* ctx, const float* mean, const float* cov, const float* scalar, const float* alpha,
+    const int32_t* start, const int32_t* end, const int32_t* gaussian_ids, const float* out,
+    float* grad_mean, float* grad_cov, float* grad_scalar, float* grad_alpha, const float* grad_out,
+    const float* topleft, uint32_t N, uint32_t N_with_dub, uint32_t tile_size, uint32_t n_tiles_h,
+    uint32_t n_tiles_w, float pixel_size_x, float pixel_size_y, uint32_t H, uint32_t W, float thresh,
+    gsb200_stream stream);
+
+/* _gs.tile_based_vol_rendering_sh (render.h:86-93, vol_render_sh.h:171-266) and
+ * _gs.tile_based_vol_rendering_sh_with_bg (render.h:119-124, vol_render_bg.h:12-129) when
+ * bg_rgb != NULL.  sh_coeffs is [N,3,C*C]; c2w: the first NINE floats are read as a packed 3x3. */
+int gsb200_tile_based_vol_rendering_sh(
+    gsb200_ctx* ctx, const float* mean, const float* cov, const float* sh_coeffs, const float* alpha,
+    const int32_t* start, const int32_t* end, const int32_t* gaussian_ids, float* out,
+    const float* topleft, const float* c2w, uint32_t N, uint32_t N_with_dub, uint32_t tile_size,
+    uint32_t n_tiles_h, uint32_t n_tiles_w, float pixel_size_x, float pixel_size_y, uint32_t H,
+    uint32_t W, uint32_t C, float thresh, const float* bg_rgb, gsb200_stream stream);
+
+/* _gs.tile_based_vol_rendering_backward_sh (render.h:95-101, vol_render_sh.h:353-480) and
+ * _gs.tile_based_vol_rendering_backward_sh_with_bg (render.h:126-132, vol_render_bg.h:131-266). */
+int gsb200_tile_based_vol_rendering_backward_sh(
+    gsb200_ctx* ctx, const float* mean, const float* cov, const float* sh_coeffs, const float* alpha,
+    const int32_t* start, const int32_t* end, const int32_t* gaussian_ids, const float* out,
+    float* grad_mean, float* grad_cov, float* grad_sh_coeffs, float* grad_alpha,
+    const float* grad_out, const float* topleft, const float* c2w, uint32_t N, uint32_t N_with_dub,
+    uint32_t tile_size, uint32_t n_tiles_h, uint32_t n_tiles_w, float pixel_size_x,
+    float pixel_size_y, uint32_t H, uint32_t W, uint32_t C, float thresh, const float* bg_rgb,
+    gsb200_stream stream);
+
+/* ================================================================================================
+ * Part 2 -- the torch-op stages of the reference hot path as single fused kernels.
+ * ============================================================================================== */
+
+/* gs.renderer.project_gaussians  gs/renderer.py:391-421 (+ project_pts :381-388, jacobian :366-378,
+ * utils/transforms.py:34-46).  h_c2w: 12 host floats (row-major [3,4]).  JW may be NULL. */
+int gsb200_project_gaussians_forward(const float* mean, const float* qvec, const float* svec,
+                                     const float* h_c2w, uint32_t N, float* mean2d, float* cov2d,
+                                     float* JW, float* depth, gsb200_stream stream);
+
+/* autograd of the above (J constant, mean2d denominator detached iff depth_detach).
+ * grad_mean[N,3] / grad_qvec[N,4] / grad_svec[N,3] are WRITTEN. */
+int gsb200_project_gaussians_backward(const float* mean, const float* qvec, const float* svec,
+                                      const float* h_c2w, uint32_t N, int depth_detach,
+                                      const float* grad_mean2d, const float* grad_cov2d,
+                                      const float* grad_depth, float* grad_mean, float* grad_qvec,
+                                      float* grad_svec, gsb200_stream stream);
+
+/* gs.culling.tile_culling_aabb_count  gs/culling.py:8-37 + utils/camera.py:301-314.
+ * Writes aabb_topleft / aabb_bottomright [N,2] int32 tile coords (x,y) and returns the duplicate
+ * count in *h_N_with_dub (synchronises, like the reference's .item()). */
+int gsb200_tile_culling_aabb_count(gsb200_ctx* ctx, const float* mean2d, const float* cov2d,
+                                   uint32_t N, uint32_t tile_size, float fx, float fy, float cx,
+                                   float cy, uint32_t W, uint32_t H, float D, int32_t* aabb_topleft,
+                                   int32_t* aabb_bottomright, int64_t* h_N_with_dub,
+                                   gsb200_stream stream);
+
+/* ================================================================================================
+ * Part 3 -- the whole view in two calls (what GaussianSplattingRenderer.render_one,
+ * gs/gaussian_splatting.py:1198-1421, and SHRenderer.forward, gs/sh_renderer.py:227-361, orchestrate
+ * from ~60 torch kernels + 5 extension calls): cull + project + AABB + count -> scan -> key emit ->
+ * radix sort -> ranges -> composite (RGB + depth + opacity + depth^2 in ONE walk, or SH).
+ * No stream compaction: culled Gaussians simply own zero duplicates, indices are global.
+ * ============================================================================================== */
+typedef struct gsb200_camera {
+  float c2w[12];              /* row-major [3,4]                                                  */
+  float fx, fy, cx, cy;
+  int32_t W, H;
+  float frustum_normals[18];  /* CameraInfo.get_frustum, utils/camera.py:260-294                  */
+  float frustum_pts[18];
+  float frustum_radius;       /* conf/base.yaml:134  (6.0)                                        */
+  float tile_radius;          /* conf/base.yaml:135  (6.0)                                        */
+  float T_thresh;             /* conf/base.yaml:136  (1e-4)                                       */
+  int32_t skip_frustum_culling;
+  int32_t depth_detach;
+} gsb200_camera;
+
+typedef struct gsb200_view_in {
+  uint32_t N;
+  const float* mean;   /* [N,3]                                                                   */
+  const float* qvec;   /* [N,4] (w,x,y,z)                                                         */
+  const float* svec;   /* [N,3] post-activation                                                   */
+  const float* alpha;  /* [N]   post-activation                                                   */
+  const float* color;  /* [N,3] post-activation RGB, or NULL when sh != NULL                      */
+  const float* sh;     /* [N,3,C*C] or NULL                                                       */
+  int32_t C;           /* SH template parameter (degree+1), 1..4                                  */
+  float sh_c2w9[9];    /* the nine floats the SH kernels read as rotation rows (A.7)              */
+  const float* bg;     /* [H,W,3] per-pixel background (RGB path) or NULL                         */
+  const float* bg_rgb; /* [3] constant background (SH path) or NULL                               */
+} gsb200_view_in;
+
+typedef struct gsb200_view_out {
+  float* rgb;      /* [H,W,3]  (includes the background term)                                     */
+  float* T;        /* [H,W]    final transmittance                                                */
+  float* depth;    /* [H,W] or NULL  (RGB path, rgb_only=False)                                   */
+  float* opacity;  /* [H,W] or NULL                                                               */
+  float* z2;       /* [H,W] or NULL  (sum w*depth^2; z_var = z2 - depth^2 is the caller's)        */
+  float* mean2d;   /* [N,2]  by-products the reference exposes to autograd / densification        */
+  float* cov2d;    /* [N,4]                                                                       */
+  float* depthg;   /* [N]                                                                         */
+  uint8_t* mask;   /* [N]                                                                         */
+  float* radii2d;  /* [N] or NULL: m + sqrt(max(m^2-det,0)) (gaussian_splatting.py:1240-1245)     */
+  int64_t* h_num_dup; /* host out (nullable): N_with_dub                                           */
+} gsb200_view_out;
+
+int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* cam, const gsb200_view_in* in,
+                          const gsb200_view_out* out, gsb200_stream stream);
+
+typedef struct gsb200_view_grads {
+  /* upstream gradients (NULL = zero) and the saved forward images */
+  const float* g_rgb;     const float* rgb;      /* [H,W,3]                                        */
+  const float* g_depth;   const float* depth;    /* [H,W]                                          */
+  const float* g_opacity; const float* opacity;
+  const float* g_z2;      const float* z2;
+  const float* T;                                 /* [H,W] (for g_bg)                               */
+  /* outputs, all WRITTEN (culled Gaussians get zeros) */
+  float* g_mean;    /* [N,3]                                                                       */
+  float* g_qvec;    /* [N,4]                                                                       */
+  float* g_svec;    /* [N,3]                                                                       */
+  float* g_alpha;   /* [N]                                                                         */
+  float* g_color;   /* [N,3] (RGB path) or NULL                                                    */
+  float* g_sh;      /* [N,3,C*C] (SH path) or NULL; must be zero-filled by the caller              */
+  float* g_mean2d;  /* [N,2] or NULL: gradient w.r.t. the projected mean (densification statistic,  */
+                    /*                gaussian_splatting.py:464-469)                                */
+  float* g_bg;      /* [H,W,3] or NULL: nan_to_num(g_rgb * T) (gs/renderer.py:1282)                 */
+} gsb200_view_grads;
+
+int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* cam, const gsb200_view_in* in,
+                           const gsb200_view_grads* g, gsb200_stream stream);
+
+/* per-view statistics of the last forward on ctx (synchronises): h_out[0]=N_with_dub,
+ * h_out[1]=number of Gaussians passing the frustum test, h_out[2]=max tile list length */
+int gsb200_view_stats(gsb200_ctx* ctx, int64_t* h_out, gsb200_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSB200_H_ */

@@ -1,0 +1,31 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE -- builds the UNMODIFIED reference `_gs` extension (gs/src/render.cu +
+# bindings.cpp) for sm_100 straight from /root/reference into oracle/_ref/_gs.so.
+# No reference source is copied into this repo; outputs go only to oracle/_ref/ (git-ignored,
+# NOT gpurun-ignored, so the .so travels to the B200 box where it is the parity checker and
+# the "reference CUDA ext" timing arm).  Recipe: SURVEY.md §8(c) (the reference's own
+# -std=c++14 must be overridden, torch 2.11 needs C++17).
+set -euo pipefail
+REF=${REF:-/root/reference}
+HERE="$(cd "$(dirname "$0")" && pwd)"
+OUT="$HERE/_ref"
+if [ ! -d "$REF/gs/src" ]; then
+  echo "build_ref: $REF/gs/src not present (GPU box?) -- using prebuilt $OUT/_gs.so if any"; exit 0
+fi
+mkdir -p "$OUT"
+if [ -f "$OUT/_gs.so" ] && [ "$OUT/_gs.so" -nt "$REF/gs/src/render.cu" ] && [ -z "${FORCE:-}" ]; then
+  echo "build_ref: $OUT/_gs.so up to date"; exit 0
+fi
+PY=${PYTHON:-python}
+TORCH_DIR=$($PY -c "import torch,os;print(os.path.dirname(torch.__file__))")
+PYINC=$($PY -c "import sysconfig;print(sysconfig.get_paths()['include'])")
+DEFS="-DTORCH_EXTENSION_NAME=_gs -DTORCH_API_INCLUDE_EXTENSION_H -D_GLIBCXX_USE_CXX11_ABI=1"
+INCS="-I$TORCH_DIR/include -I$TORCH_DIR/include/torch/csrc/api/include -I$PYINC -I$REF/gs/src/include -I$REF/gs/src"
+nvcc -O3 -std=c++17 -gencode arch=compute_100,code=sm_100 --expt-relaxed-constexpr $DEFS \
+     -Xcompiler -fPIC $INCS -c "$REF/gs/src/render.cu" -o "$OUT/render.o"
+g++ -O2 -std=c++17 -fPIC $DEFS $INCS -I/usr/local/cuda/include -c "$REF/gs/src/bindings.cpp" -o "$OUT/bindings.o"
+g++ -shared "$OUT/render.o" "$OUT/bindings.o" -L"$TORCH_DIR/lib" -L/usr/local/cuda/lib64 \
+    -lc10 -ltorch_cpu -ltorch -ltorch_python -lc10_cuda -ltorch_cuda -lcudart \
+    -Wl,-rpath,"$TORCH_DIR/lib" -o "$OUT/_gs.so"
+rm -f "$OUT/render.o" "$OUT/bindings.o"
+echo "build_ref: built $OUT/_gs.so"
