@@ -1,0 +1,435 @@
+// api.cu -- the extern "C" surface of libgsb200.so (include/gsb200.h).  Argument validation mirrors the
+// reference's TORCH_CHECK contracts (gs/src/include/common.h:29-54) but reports through return codes.
+#include <stdarg.h>
+
+#include "kernels.cuh"
+
+namespace gsb {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static Camera make_camera(const float* c2w12, float fx, float fy, float cx, float cy, int W, int H) {
+  Camera c;
+  memset(&c, 0, sizeof(c));
+  for (int r = 0; r < 3; ++r) {
+    for (int k = 0; k < 3; ++k) c.R[3 * r + k] = c2w12[4 * r + k];
+    c.t[r] = c2w12[4 * r + 3];
+  }
+  c.fx = fx; c.fy = fy; c.cx = cx; c.cy = cy;
+  c.W = W; c.H = H;
+  c.tiles_w = (W + 15) / 16;
+  c.tiles_h = (H + 15) / 16;
+  c.frustum_radius = 6.0f; c.tile_radius = 6.0f;
+  c.skip_frustum = 1; c.depth_detach = 1;
+  return c;
+}
+
+static Camera camera_from_abi(const gsb200_camera* in) {
+  Camera c = make_camera(in->c2w, in->fx, in->fy, in->cx, in->cy, in->W, in->H);
+  memcpy(c.fn, in->frustum_normals, sizeof(c.fn));
+  memcpy(c.fp, in->frustum_pts, sizeof(c.fp));
+  c.frustum_radius = in->frustum_radius;
+  c.tile_radius = in->tile_radius;
+  c.skip_frustum = in->skip_frustum_culling;
+  c.depth_detach = in->depth_detach;
+  return c;
+}
+
+static int check_tile(uint32_t tile_size, uint32_t th, uint32_t tw, uint32_t H, uint32_t W) {
+  GSB_CHECK(tile_size == 16, GSB200_ERR_UNSUPPORTED, "tile_size %u unsupported (libgsb200 is specialised for 16)",
+            tile_size);
+  GSB_CHECK(th == (H + 15) / 16 && tw == (W + 15) / 16, GSB200_ERR_INVALID,
+            "n_tiles (%u,%u) inconsistent with image %ux%u", th, tw, H, W);
+  return GSB200_OK;
+}
+
+static int set_device(gsb200_ctx* ctx) {
+  GSB_CHECK(ctx != nullptr, GSB200_ERR_INVALID, "null context");
+  GSB_CUDA(cudaSetDevice(ctx->device));
+  return GSB200_OK;
+}
+
+// records for the reference-compatible composite ops: pack (mean2d, cov2d, alpha, payload) into the arena
+static int pack_for_compat(gsb200_ctx* ctx, uint32_t N, const float* mean, const float* cov, const float* alpha,
+                           const float* payload, int pay_kind, cudaStream_t st) {
+  int rc;
+  if ((rc = ctx->splat.reserve((size_t)N * sizeof(Splat)))) return rc;
+  if (pay_kind != 0 && (rc = ctx->pay.reserve((size_t)N * 16))) return rc;
+  return launch_pack_splats(N, mean, cov, alpha, payload, pay_kind, ctx->splat.as<Splat>(), ctx->pay.as<float4>(), st);
+}
+
+static void fill_common(CompositeArgs& a, gsb200_ctx* ctx, const int32_t* start, const int32_t* end,
+                        const int32_t* ids, const float* topleft, uint32_t th, uint32_t tw, float psx, float psy,
+                        uint32_t H, uint32_t W, float thresh) {
+  a.splat = ctx->splat.as<Splat>();
+  a.pay = ctx->pay.as<float4>();
+  a.ids = ids; a.start = start; a.end = end;
+  a.topleft_ptr = topleft;
+  a.psx = psx; a.psy = psy;
+  a.H = (int)H; a.W = (int)W; a.tiles_w = (int)tw; a.tiles_h = (int)th;
+  a.thresh = thresh;
+  a.device = ctx->device;
+}
+
+}  // namespace gsb
+
+using namespace gsb;
+
+extern "C" {
+
+const char* gsb200_last_error(void) { return g_err; }
+int gsb200_version(void) { return 100; }
+
+int gsb200_ctx_create(int device, gsb200_ctx** out) {
+  GSB_CHECK(out != nullptr, GSB200_ERR_INVALID, "null out pointer");
+  GSB_CUDA(cudaSetDevice(device));
+  gsb200_ctx* c = new gsb200_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  GSB_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  GSB_CUDA(cudaHostAlloc((void**)&c->h_total, 4 * sizeof(int64_t), cudaHostAllocDefault));
+  *out = c;
+  return GSB200_OK;
+}
+
+int gsb200_ctx_destroy(gsb200_ctx* c) {
+  if (!c) return GSB200_OK;
+  cudaSetDevice(c->device);
+  gsb::Buf* bufs[] = {&c->splat, &c->pay, &c->rect, &c->count, &c->incl, &c->ggeom, &c->gpay, &c->keys[0],
+                      &c->keys[1], &c->vals[0], &c->vals[1], &c->cub_tmp, &c->start, &c->end, &c->d_total};
+  for (auto* b : bufs) b->release();
+  if (c->h_total) cudaFreeHost(c->h_total);
+  delete c;
+  return GSB200_OK;
+}
+
+// ---- Part 1 -------------------------------------------------------------------------------------------
+int gsb200_culling_gaussian_bsphere(const float* mean, const float* qvec, const float* svec, const float* normal,
+                                    const float* pts, uint8_t* mask, uint32_t N, float thresh, gsb200_stream stream) {
+  (void)qvec;
+  GSB_CHECK(N == 0 || (mean && svec && normal && pts && mask), GSB200_ERR_INVALID, "culling_gaussian_bsphere: null tensor");
+  return launch_cull_bsphere(N, mean, svec, normal, pts, mask, thresh, (cudaStream_t)stream);
+}
+
+int gsb200_tile_culling_aabb_start_end(gsb200_ctx* ctx, const int32_t* tl, const int32_t* br, int32_t* gaussian_ids,
+                                       int32_t* start, int32_t* end, const float* depth, uint32_t N, uint32_t D,
+                                       uint32_t th, uint32_t tw, gsb200_stream stream) {
+  int rc;
+  if ((rc = set_device(ctx))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  GSB_CHECK(start && end, GSB200_ERR_INVALID, "tile_culling_aabb_start_end: null start/end");
+  GSB_CHECK(tw <= 65535 && th <= 65535, GSB200_ERR_UNSUPPORTED, "tile grid too large");
+  if (N > 0) {
+    GSB_CHECK(tl && br && depth, GSB200_ERR_INVALID, "tile_culling_aabb_start_end: null tensor");
+    if ((rc = ctx->count.reserve((size_t)N * 4))) return rc;
+    if ((rc = ctx->incl.reserve((size_t)N * 4))) return rc;
+    if ((rc = ctx->rect.reserve((size_t)N * 8))) return rc;
+    if ((rc = launch_count_from_aabb(N, tl, br, ctx->count.as<int32_t>(), ctx->rect.as<ushort4>(), st))) return rc;
+    if ((rc = scan_counts(ctx, N, st))) return rc;
+  }
+  int64_t total = 0;
+  if (N > 0 && (rc = read_total(ctx, N, &total, st))) return rc;
+  // the reference asserts size_h == N_with_dub on the host (aabb_culling.h:228)
+  GSB_CHECK(total == (int64_t)D, GSB200_ERR_MISMATCH,
+            "tile_culling_aabb_start_end: AABBs expand to %lld duplicates but gaussian_ids has %u entries",
+            (long long)total, D);
+  GSB_CHECK(D == 0 || gaussian_ids, GSB200_ERR_INVALID, "null gaussian_ids");
+  return bin_and_sort(ctx, N, (int64_t)D, depth, (int)th, (int)tw, gaussian_ids, start, end, st);
+}
+
+int gsb200_tile_based_vol_rendering_start_end_with_T(
+    gsb200_ctx* ctx, const float* mean, const float* cov, const float* color, const float* alpha, const int32_t* start,
+    const int32_t* end, const int32_t* ids, float* out, const float* topleft, uint32_t N, uint32_t D,
+    uint32_t tile_size, uint32_t th, uint32_t tw, float psx, float psy, uint32_t H, uint32_t W, float thresh,
+    float* T, gsb200_stream stream) {
+  (void)D;
+  int rc;
+  if ((rc = set_device(ctx))) return rc;
+  if ((rc = check_tile(tile_size, th, tw, H, W))) return rc;
+  GSB_CHECK(out && start && end && topleft, GSB200_ERR_INVALID, "vol_rendering: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = pack_for_compat(ctx, N, mean, cov, alpha, color, 1, st))) return rc;
+  CompositeArgs a;
+  fill_common(a, ctx, start, end, ids, topleft, th, tw, psx, psy, H, W, thresh);
+  a.out = out; a.T = T;
+  return launch_composite_fwd(PAY_RGB, 1, false, a, st);
+}
+
+int gsb200_tile_based_vol_rendering_backward_start_end(
+    gsb200_ctx* ctx, const float* mean, const float* cov, const float* color, const float* alpha, const int32_t* start,
+    const int32_t* end, const int32_t* ids, const float* out, float* grad_mean, float* grad_cov, float* grad_color,
+    float* grad_alpha, const float* grad_out, const float* topleft, uint32_t N, uint32_t D, uint32_t tile_size,
+    uint32_t th, uint32_t tw, float psx, float psy, uint32_t H, uint32_t W, float thresh, gsb200_stream stream) {
+  (void)D;
+  int rc;
+  if ((rc = set_device(ctx))) return rc;
+  if ((rc = check_tile(tile_size, th, tw, H, W))) return rc;
+  GSB_CHECK(out && grad_out && grad_mean && grad_cov && grad_color && grad_alpha && topleft, GSB200_ERR_INVALID,
+            "vol_rendering_backward: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = pack_for_compat(ctx, N, mean, cov, alpha, color, 1, st))) return rc;
+  CompositeArgs a;
+  fill_common(a, ctx, start, end, ids, topleft, th, tw, psx, psy, H, W, thresh);
+  a.fin = out; a.gout = grad_out;
+  a.grad_mean = grad_mean; a.grad_cov = grad_cov; a.grad_pay = grad_color; a.grad_alpha = grad_alpha;
+  return launch_composite_bwd(PAY_RGB, 1, false, false, a, st);
+}
+
+int gsb200_tile_based_vol_rendering_scalar(
+    gsb200_ctx* ctx, const float* mean, const float* cov, const float* scalar, const float* alpha, const int32_t* start,
+    const int32_t* end, const int32_t* ids, float* out, const float* topleft, uint32_t N, uint32_t D,
+    uint32_t tile_size, uint32_t th, uint32_t tw, float psx, float psy, uint32_t H, uint32_t W, float thresh,
+    float* T, gsb200_stream stream) {
+  (void)D;
+  int rc;
+  if ((rc = set_device(ctx))) return rc;
+  if ((rc = check_tile(tile_size, th, tw, H, W))) return rc;
+  GSB_CHECK(out && start && end && topleft, GSB200_ERR_INVALID, "vol_rendering_scalar: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = pack_for_compat(ctx, N, mean, cov, alpha, scalar, 2, st))) return rc;
+  CompositeArgs a;
+  fill_common(a, ctx, start, end, ids, topleft, th, tw, psx, psy, H, W, thresh);
+  a.out = out; a.T = T;
+  return launch_composite_fwd(PAY_SCALAR, 1, false, a, st);
+}
+
+int gsb200_tile_based_vol_rendering_scalar_backward(
+    gsb200_ctx* ctx, const float* mean, const float* cov, const float* scalar, const float* alpha, const int32_t* start,
+    const int32_t* end, const int32_t* ids, const float* out, float* grad_mean, float* grad_cov, float* grad_scalar,
+    float* grad_alpha, const float* grad_out, const float* topleft, uint32_t N, uint32_t D, uint32_t tile_size,
+    uint32_t th, uint32_t tw, float psx, float psy, uint32_t H, uint32_t W, float thresh, gsb200_stream stream) {
+  (void)D;
+  int rc;
+  if ((rc = set_device(ctx))) return rc;
+  if ((rc = check_tile(tile_size, th, tw, H, W))) return rc;
+  GSB_CHECK(out && grad_out && grad_mean && grad_cov && grad_scalar && grad_alpha && topleft, GSB200_ERR_INVALID,
+            "vol_rendering_scalar_backward: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = pack_for_compat(ctx, N, mean, cov, alpha, scalar, 2, st))) return rc;
+  CompositeArgs a;
+  fill_common(a, ctx, start, end, ids, topleft, th, tw, psx, psy, H, W, thresh);
+  a.fin = out; a.gout = grad_out;
+  a.grad_mean = grad_mean; a.grad_cov = grad_cov; a.grad_pay = grad_scalar; a.grad_alpha = grad_alpha;
+  return launch_composite_bwd(PAY_SCALAR, 1, false, false, a, st);
+}
+
+int gsb200_tile_based_vol_rendering_sh(
+    gsb200_ctx* ctx, const float* mean, const float* cov, const float* sh, const float* alpha, const int32_t* start,
+    const int32_t* end, const int32_t* ids, float* out, const float* topleft, const float* c2w, uint32_t N, uint32_t D,
+    uint32_t tile_size, uint32_t th, uint32_t tw, float psx, float psy, uint32_t H, uint32_t W, uint32_t C,
+    float thresh, const float* bg_rgb, gsb200_stream stream) {
+  (void)D;
+  int rc;
+  if ((rc = set_device(ctx))) return rc;
+  if ((rc = check_tile(tile_size, th, tw, H, W))) return rc;
+  GSB_CHECK(C >= 1 && C <= 4, GSB200_ERR_UNSUPPORTED, "SH C=%u unsupported (reference dispatches 1..4, render.cu:507-545)", C);
+  GSB_CHECK(out && start && end && topleft && c2w && (N == 0 || sh), GSB200_ERR_INVALID, "vol_rendering_sh: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = pack_for_compat(ctx, N, mean, cov, alpha, nullptr, 0, st))) return rc;
+  CompositeArgs a;
+  fill_common(a, ctx, start, end, ids, topleft, th, tw, psx, psy, H, W, thresh);
+  a.sh = sh; a.c9_ptr = c2w; a.bg_rgb = bg_rgb;
+  a.out = out;
+  return launch_composite_fwd(PAY_SH, (int)C, false, a, st);
+}
+
+int gsb200_tile_based_vol_rendering_backward_sh(
+    gsb200_ctx* ctx, const float* mean, const float* cov, const float* sh, const float* alpha, const int32_t* start,
+    const int32_t* end, const int32_t* ids, const float* out, float* grad_mean, float* grad_cov, float* grad_sh,
+    float* grad_alpha, const float* grad_out, const float* topleft, const float* c2w, uint32_t N, uint32_t D,
+    uint32_t tile_size, uint32_t th, uint32_t tw, float psx, float psy, uint32_t H, uint32_t W, uint32_t C,
+    float thresh, const float* bg_rgb, gsb200_stream stream) {
+  (void)D;
+  int rc;
+  if ((rc = set_device(ctx))) return rc;
+  if ((rc = check_tile(tile_size, th, tw, H, W))) return rc;
+  GSB_CHECK(C >= 1 && C <= 4, GSB200_ERR_UNSUPPORTED, "SH C=%u unsupported", C);
+  GSB_CHECK(out && grad_out && grad_mean && grad_cov && grad_sh && grad_alpha && topleft && c2w, GSB200_ERR_INVALID,
+            "vol_rendering_backward_sh: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = pack_for_compat(ctx, N, mean, cov, alpha, nullptr, 0, st))) return rc;
+  CompositeArgs a;
+  fill_common(a, ctx, start, end, ids, topleft, th, tw, psx, psy, H, W, thresh);
+  a.sh = sh; a.c9_ptr = c2w; a.bg_rgb = bg_rgb;
+  a.fin = out; a.gout = grad_out;
+  a.grad_mean = grad_mean; a.grad_cov = grad_cov; a.grad_pay = grad_sh; a.grad_alpha = grad_alpha;
+  return launch_composite_bwd(PAY_SH, (int)C, false, false, a, st);
+}
+
+// ---- Part 2 -------------------------------------------------------------------------------------------
+int gsb200_project_gaussians_forward(const float* mean, const float* qvec, const float* svec, const float* h_c2w,
+                                     uint32_t N, float* mean2d, float* cov2d, float* JW, float* depth,
+                                     gsb200_stream stream) {
+  GSB_CHECK(h_c2w && (N == 0 || (mean && qvec && svec && mean2d && cov2d && depth)), GSB200_ERR_INVALID,
+            "project_gaussians_forward: null tensor");
+  Camera cam = make_camera(h_c2w, 1.f, 1.f, 0.f, 0.f, 16, 16);
+  return launch_project_fwd(N, mean, qvec, svec, cam, mean2d, cov2d, JW, depth, (cudaStream_t)stream);
+}
+
+int gsb200_project_gaussians_backward(const float* mean, const float* qvec, const float* svec, const float* h_c2w,
+                                      uint32_t N, int depth_detach, const float* g_m2, const float* g_cov,
+                                      const float* g_depth, float* g_mean, float* g_qvec, float* g_svec,
+                                      gsb200_stream stream) {
+  GSB_CHECK(h_c2w && (N == 0 || (mean && qvec && svec && g_mean && g_qvec && g_svec)), GSB200_ERR_INVALID,
+            "project_gaussians_backward: null tensor");
+  Camera cam = make_camera(h_c2w, 1.f, 1.f, 0.f, 0.f, 16, 16);
+  cam.depth_detach = depth_detach;
+  return launch_project_bwd(N, mean, qvec, svec, cam, g_m2, g_cov, g_depth, g_mean, g_qvec, g_svec,
+                            (cudaStream_t)stream);
+}
+
+int gsb200_tile_culling_aabb_count(gsb200_ctx* ctx, const float* mean2d, const float* cov2d, uint32_t N,
+                                   uint32_t tile_size, float fx, float fy, float cx, float cy, uint32_t W, uint32_t H,
+                                   float D, int32_t* tl, int32_t* br, int64_t* h_total, gsb200_stream stream) {
+  int rc;
+  if ((rc = set_device(ctx))) return rc;
+  GSB_CHECK(tile_size >= 1, GSB200_ERR_INVALID, "tile_size must be positive");
+  GSB_CHECK(h_total != nullptr, GSB200_ERR_INVALID, "null h_N_with_dub");
+  *h_total = 0;
+  if (N == 0) return GSB200_OK;
+  GSB_CHECK(mean2d && cov2d && tl && br, GSB200_ERR_INVALID, "tile_culling_aabb_count: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = ctx->count.reserve((size_t)N * 4))) return rc;
+  if ((rc = ctx->incl.reserve((size_t)N * 4))) return rc;
+  if ((rc = launch_aabb_count(N, mean2d, cov2d, (int)tile_size, fx, fy, cx, cy, (int)W, (int)H, D, tl, br,
+                              ctx->count.as<int32_t>(), st)))
+    return rc;
+  if ((rc = scan_counts(ctx, N, st))) return rc;
+  return read_total(ctx, N, h_total, st);
+}
+
+// ---- Part 3 -------------------------------------------------------------------------------------------
+int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb200_view_in* in,
+                          const gsb200_view_out* out, gsb200_stream stream) {
+  int rc;
+  if ((rc = set_device(ctx))) return rc;
+  GSB_CHECK(camin && in && out, GSB200_ERR_INVALID, "render_forward: null argument");
+  GSB_CHECK(out->rgb && out->mean2d && out->cov2d && out->depthg && out->mask, GSB200_ERR_INVALID,
+            "render_forward: rgb / mean2d / cov2d / depthg / mask outputs are required");
+  const bool is_sh = in->sh != nullptr;
+  GSB_CHECK(is_sh || in->color, GSB200_ERR_INVALID, "render_forward: need color or sh");
+  GSB_CHECK(!is_sh || (in->C >= 1 && in->C <= 4), GSB200_ERR_UNSUPPORTED, "SH C=%d unsupported", in->C);
+  const bool extras = !is_sh && out->depth && out->opacity && out->z2;
+  GSB_CHECK(is_sh || extras || (!out->depth && !out->opacity && !out->z2), GSB200_ERR_INVALID,
+            "render_forward: depth / opacity / z2 must be given together");
+  cudaStream_t st = (cudaStream_t)stream;
+  Camera cam = camera_from_abi(camin);
+  GSB_CHECK(cam.tiles_w <= 65535 && cam.tiles_h <= 65535, GSB200_ERR_UNSUPPORTED, "tile grid too large");
+  const uint32_t N = in->N;
+  const uint32_t T = (uint32_t)cam.tiles_w * cam.tiles_h;
+  if ((rc = ctx->start.reserve((size_t)T * 4))) return rc;
+  if ((rc = ctx->end.reserve((size_t)T * 4))) return rc;
+  int64_t D = 0;
+  if (N > 0) {
+    GSB_CHECK(in->mean && in->qvec && in->svec && in->alpha, GSB200_ERR_INVALID, "render_forward: null parameter tensor");
+    if ((rc = ctx->splat.reserve((size_t)N * sizeof(Splat)))) return rc;
+    if (!is_sh && (rc = ctx->pay.reserve((size_t)N * 16))) return rc;
+    if ((rc = ctx->rect.reserve((size_t)N * 8))) return rc;
+    if ((rc = ctx->count.reserve((size_t)N * 4))) return rc;
+    if ((rc = ctx->incl.reserve((size_t)N * 4))) return rc;
+    if ((rc = launch_preprocess(N, in->mean, in->qvec, in->svec, in->alpha, is_sh ? nullptr : in->color, cam,
+                                out->mean2d, out->cov2d, out->depthg, out->mask, out->radii2d,
+                                ctx->splat.as<Splat>(), ctx->pay.as<float4>(), ctx->rect.as<ushort4>(),
+                                ctx->count.as<int32_t>(), st)))
+      return rc;
+    if ((rc = scan_counts(ctx, N, st))) return rc;
+    if ((rc = read_total(ctx, N, &D, st))) return rc;  // the one host sync of the view (reference: two + 5 mallocs)
+  }
+  if (out->h_num_dup) *out->h_num_dup = D;
+  if ((rc = bin_and_sort(ctx, N, D, out->depthg, cam.tiles_h, cam.tiles_w, nullptr, ctx->start.as<int32_t>(),
+                         ctx->end.as<int32_t>(), st)))
+    return rc;
+  ctx->N = N; ctx->cam = cam; ctx->mode = is_sh ? PAY_SH : PAY_RGB; ctx->C = is_sh ? in->C : 1;
+
+  CompositeArgs a;
+  a.splat = ctx->splat.as<Splat>();
+  a.pay = ctx->pay.as<float4>();
+  a.sh = in->sh;
+  a.ids = ctx->vals[ctx->sorted_sel].as<int32_t>();
+  a.start = ctx->start.as<int32_t>(); a.end = ctx->end.as<int32_t>();
+  a.tlx = -cam.cx / cam.fx; a.tly = -cam.cy / cam.fy;  // gaussian_splatting.py:1274-1276
+  a.psx = 1.0f / cam.fx; a.psy = 1.0f / cam.fy;
+  a.H = cam.H; a.W = cam.W; a.tiles_w = cam.tiles_w; a.tiles_h = cam.tiles_h;
+  a.thresh = camin->T_thresh;
+  memcpy(a.c9, in->sh_c2w9, sizeof(a.c9));
+  a.bg = in->bg; a.bg_rgb = in->bg_rgb;
+  a.device = ctx->device;
+  a.write_empty = 1;
+  a.out = out->rgb; a.T = out->T;
+  a.depth = out->depth; a.opacity = out->opacity; a.z2 = out->z2;
+  return launch_composite_fwd(is_sh ? PAY_SH : PAY_RGB, is_sh ? in->C : 1, extras, a, st);
+}
+
+int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb200_view_in* in,
+                           const gsb200_view_grads* g, gsb200_stream stream) {
+  int rc;
+  if ((rc = set_device(ctx))) return rc;
+  GSB_CHECK(camin && in && g, GSB200_ERR_INVALID, "render_backward: null argument");
+  const bool is_sh = in->sh != nullptr;
+  GSB_CHECK(ctx->N == in->N && ctx->mode == (is_sh ? PAY_SH : PAY_RGB), GSB200_ERR_INVALID,
+            "render_backward: context does not hold the forward state of this view (N=%u vs %u)", ctx->N, in->N);
+  GSB_CHECK(g->rgb && g->mask && g->g_mean && g->g_qvec && g->g_svec && g->g_alpha, GSB200_ERR_INVALID,
+            "render_backward: rgb, mask and g_mean/g_qvec/g_svec/g_alpha are required");
+  GSB_CHECK(is_sh ? (g->g_sh != nullptr) : (g->g_color != nullptr), GSB200_ERR_INVALID,
+            "render_backward: g_sh (SH path) or g_color (RGB path) is required");
+  cudaStream_t st = (cudaStream_t)stream;
+  Camera cam = camera_from_abi(camin);
+  const uint32_t N = in->N;
+  if (N == 0) return GSB200_OK;
+  const bool extras = !is_sh && (g->g_depth || g->g_opacity || g->g_z2);
+  GSB_CHECK(!extras || (g->depth && g->opacity && g->z2), GSB200_ERR_INVALID,
+            "render_backward: saved depth / opacity / z2 images are required with their gradients");
+  if ((rc = ctx->ggeom.reserve((size_t)N * 32))) return rc;
+  GSB_CUDA(cudaMemsetAsync(ctx->ggeom.p, 0, (size_t)N * 32, st));
+  if (!is_sh) {
+    if ((rc = ctx->gpay.reserve((size_t)N * 16))) return rc;
+    GSB_CUDA(cudaMemsetAsync(ctx->gpay.p, 0, (size_t)N * 16, st));
+  }
+  CompositeArgs a;
+  a.splat = ctx->splat.as<Splat>();
+  a.pay = ctx->pay.as<float4>();
+  a.sh = in->sh;
+  a.ids = ctx->vals[ctx->sorted_sel].as<int32_t>();
+  a.start = ctx->start.as<int32_t>(); a.end = ctx->end.as<int32_t>();
+  a.tlx = -cam.cx / cam.fx; a.tly = -cam.cy / cam.fy;
+  a.psx = 1.0f / cam.fx; a.psy = 1.0f / cam.fy;
+  a.H = cam.H; a.W = cam.W; a.tiles_w = cam.tiles_w; a.tiles_h = cam.tiles_h;
+  a.thresh = camin->T_thresh;
+  memcpy(a.c9, in->sh_c2w9, sizeof(a.c9));
+  a.bg = in->bg; a.bg_rgb = in->bg_rgb;
+  a.device = ctx->device;
+  a.fin = g->rgb; a.gout = g->g_rgb;
+  a.fin_depth = g->depth; a.g_depth = g->g_depth;
+  a.fin_opacity = g->opacity; a.g_opacity = g->g_opacity;
+  a.fin_z2 = g->z2; a.g_z2 = g->g_z2;
+  a.ggeom = ctx->ggeom.as<float>();
+  a.gpay = ctx->gpay.as<float>();
+  a.grad_pay = g->g_sh;
+  a.g_bg = g->g_bg;
+  if (ctx->D > 0 || g->g_bg) {
+    if ((rc = launch_composite_bwd(is_sh ? PAY_SH : PAY_RGB, is_sh ? in->C : 1, extras, true, a, st))) return rc;
+  }
+  return launch_project_bwd_fused(N, in->mean, in->qvec, in->svec, g->mask, cam, ctx->ggeom.as<float4>(),
+                                  is_sh ? nullptr : ctx->gpay.as<float4>(), g->g_mean, g->g_qvec, g->g_svec,
+                                  g->g_alpha, is_sh ? nullptr : g->g_color, g->g_mean2d, st);
+}
+
+int gsb200_view_stats(gsb200_ctx* ctx, int64_t* h_out, gsb200_stream stream) {
+  int rc;
+  if ((rc = set_device(ctx))) return rc;
+  GSB_CHECK(h_out, GSB200_ERR_INVALID, "null h_out");
+  GSB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  h_out[0] = ctx->D;
+  h_out[1] = -1;
+  h_out[2] = -1;
+  return GSB200_OK;
+}
+
+}  // extern "C"

@@ -238,8 +238,8 @@ GSB_HD Splat make_splat(const float m2[2], const float cov[4], float alpha) {
   } else {
     double qmax = 2.0 * log(a255) * (1.0 + 1e-6) + 1e-6;
     double dq = A * Cc - B * B;  // det(S^-1)
-    s.hx = (float)(sqrt(qmax * Cc / dq) * (1.0 + 1e-4)) + 1e-12f;
-    s.hy = (float)(sqrt(qmax * A / dq) * (1.0 + 1e-4)) + 1e-12f;
+    s.hx = (float)(sqrt(qmax * Cc / dq) * (1.0 + 1e-4)) + 1e-6f;
+    s.hy = (float)(sqrt(qmax * A / dq) * (1.0 + 1e-4)) + 1e-6f;
   }
   return s;
 }

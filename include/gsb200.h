@@ -25,6 +25,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the only exported symbols of libgsb200.so */
+#endif
 
 #define GSB200_OK 0
 #define GSB200_ERR_INVALID 1     /* contract violation (TORCH_CHECK in the reference)            */
@@ -206,6 +209,7 @@ typedef struct gsb200_view_grads {
   const float* g_opacity; const float* opacity;
   const float* g_z2;      const float* z2;
   const float* T;                                 /* [H,W] (for g_bg)                               */
+  const uint8_t* mask;                            /* [N] frustum mask written by the forward        */
   /* outputs, all WRITTEN (culled Gaussians get zeros) */
   float* g_mean;    /* [N,3]                                                                       */
   float* g_qvec;    /* [N,4]                                                                       */
@@ -225,6 +229,9 @@ int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* cam, const gsb2
  * h_out[1]=number of Gaussians passing the frustum test, h_out[2]=max tile list length */
 int gsb200_view_stats(gsb200_ctx* ctx, int64_t* h_out, gsb200_stream stream);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,90 @@
+// hostmath.cpp -- TEST INFRASTRUCTURE.  Compiles gsgen_b200/csrc/gsb200_math.cuh (the host+device
+// per-Gaussian math the CUDA kernels use) with g++ so the CPU test-suite can check it against the
+// oracle without a GPU.  Never loaded by the product path.
+#include "../../gsgen_b200/csrc/gsb200_math.cuh"
+
+using namespace gsb;
+
+static Camera make_cam(const float* c2w12, int depth_detach) {
+  Camera c{};
+  for (int r = 0; r < 3; ++r) {
+    for (int k = 0; k < 3; ++k) c.R[3 * r + k] = c2w12[4 * r + k];
+    c.t[r] = c2w12[4 * r + 3];
+  }
+  c.depth_detach = depth_detach;
+  return c;
+}
+
+extern "C" {
+
+void hm_project_fwd(int N, const float* mean, const float* qvec, const float* svec, const float* c2w12,
+                    float* mean2d, float* cov2d, float* depth) {
+  Camera cam = make_cam(c2w12, 1);
+  for (int i = 0; i < N; ++i) {
+    Proj f;
+    project_gaussian(mean + 3 * i, qvec + 4 * i, svec + 3 * i, cam, f);
+    mean2d[2 * i] = f.mean2d[0]; mean2d[2 * i + 1] = f.mean2d[1];
+    for (int k = 0; k < 4; ++k) cov2d[4 * i + k] = f.cov[k];
+    depth[i] = f.depth;
+  }
+}
+
+void hm_project_bwd(int N, const float* mean, const float* qvec, const float* svec, const float* c2w12,
+                    int depth_detach, const float* g_m2, const float* g_cov, const float* g_depth, float* g_mean,
+                    float* g_qvec, float* g_svec) {
+  Camera cam = make_cam(c2w12, depth_detach);
+  for (int i = 0; i < N; ++i) {
+    Proj f;
+    project_gaussian(mean + 3 * i, qvec + 4 * i, svec + 3 * i, cam, f);
+    project_gaussian_bwd(svec + 3 * i, cam, f, g_m2 + 2 * i, g_cov + 4 * i, g_depth[i], g_mean + 3 * i,
+                         g_qvec + 4 * i, g_svec + 3 * i);
+  }
+}
+
+void hm_aabb(int N, const float* mean2d, const float* cov2d, float D, float fx, float fy, float cx, float cy, int W,
+             int H, int tile, int* tl, int* br) {
+  for (int i = 0; i < N; ++i) {
+    int r[4];
+    aabb_tiles(mean2d + 2 * i, cov2d[4 * i], cov2d[4 * i + 3], D, fx, fy, cx, cy, W, H, tile, r);
+    tl[2 * i] = r[0]; tl[2 * i + 1] = r[1]; br[2 * i] = r[2]; br[2 * i + 1] = r[3];
+  }
+}
+
+int hm_cull(int N, const float* mean, const float* svec, const float* fn, const float* fp, float thresh,
+            unsigned char* mask) {
+  int n = 0;
+  for (int i = 0; i < N; ++i) {
+    float r = fmaxf(fmaxf(svec[3 * i], svec[3 * i + 1]), svec[3 * i + 2]) * thresh;
+    mask[i] = sphere_in_frustum(mean + 3 * i, r, fn, fp) ? 1 : 0;
+    n += mask[i];
+  }
+  return n;
+}
+
+// a*G of splat records at query points (exp2 evaluated with exp2f here; the kernels use MUFU.EX2), plus the
+// bounding-box half extents and the gradient direction v = S^-1 d used by the backward
+void hm_splat_eval(int N, const float* mean2d, const float* cov2d, const float* alpha, const float* query /*[N,2]*/,
+                   float* aG, float* G, float* vx, float* vy, float* hx, float* hy) {
+  for (int i = 0; i < N; ++i) {
+    Splat s = make_splat(mean2d + 2 * i, cov2d + 4 * i, alpha[i]);
+    float dx = query[2 * i] - s.mx, dy = query[2 * i + 1] - s.my;
+    float u = fmaf(s.p0, dx, s.p1 * dy), v = s.p2 * dy;
+    float g = exp2f(fmaf(-u, u, -(v * v)));
+    G[i] = g; aG[i] = s.a * g;
+    vx[i] = kInvCholScale2 * s.p0 * u;
+    vy[i] = kInvCholScale2 * fmaf(s.p1, u, s.p2 * v);
+    hx[i] = s.hx; hy[i] = s.hy;
+  }
+}
+
+void hm_sh_basis(int C, const float* pos2, const float* c9, float* out16) {
+  float d[3];
+  pixel_dir(pos2[0], pos2[1], c9, d);
+  switch (C) {
+    case 1: sh_basis<1>(d[0], d[1], d[2], out16); break;
+    case 2: sh_basis<2>(d[0], d[1], d[2], out16); break;
+    case 3: sh_basis<3>(d[0], d[1], d[2], out16); break;
+    default: sh_basis<4>(d[0], d[1], d[2], out16); break;
+  }
+}
+}
