@@ -77,6 +77,24 @@ static void fill_common(CompositeArgs& a, gsb200_ctx* ctx, const int32_t* start,
   a.device = ctx->device;
 }
 
+static int next_evset(gsb200_ctx::EvSet** sets, int* cap, int* used, gsb200_ctx::EvSet** out) {
+  if (*used == *cap) {
+    int ncap = *cap ? *cap * 2 : 64;
+    gsb200_ctx::EvSet* ns = new gsb200_ctx::EvSet[ncap];
+    for (int i = 0; i < *cap; ++i) ns[i] = (*sets)[i];
+    for (int i = *cap; i < ncap; ++i)
+      for (int k = 0; k < 5; ++k) GSB_CUDA(cudaEventCreate(&ns[i].e[k]));
+    delete[] *sets;
+    *sets = ns; *cap = ncap;
+  }
+  *out = &(*sets)[(*used)++];
+  return GSB200_OK;
+}
+#define GSB_EV(set, k, st)                                   \
+  do {                                                       \
+    if (set) GSB_CUDA(cudaEventRecord((set)->e[k], st));     \
+  } while (0)
+
 }  // namespace gsb
 
 using namespace gsb;
@@ -327,6 +345,9 @@ int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb
   if ((rc = ctx->start.reserve((size_t)T * 4))) return rc;
   if ((rc = ctx->end.reserve((size_t)T * 4))) return rc;
   int64_t D = 0;
+  gsb200_ctx::EvSet* ev = nullptr;
+  if (ctx->profiling && (rc = next_evset(&ctx->fwd_sets, &ctx->fwd_cap, &ctx->fwd_used, &ev))) return rc;
+  GSB_EV(ev, 0, st);
   if (N > 0) {
     GSB_CHECK(in->mean && in->qvec && in->svec && in->alpha, GSB200_ERR_INVALID, "render_forward: null parameter tensor");
     if ((rc = ctx->splat.reserve((size_t)N * sizeof(Splat)))) return rc;
@@ -339,14 +360,26 @@ int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb
                                 ctx->splat.as<Splat>(), ctx->pay.as<float4>(), ctx->rect.as<ushort4>(),
                                 ctx->count.as<int32_t>(), st)))
       return rc;
+    GSB_EV(ev, 1, st);
     if ((rc = scan_counts(ctx, N, st))) return rc;
     if ((rc = read_total(ctx, N, &D, st))) return rc;  // the one host sync of the view (reference: two + 5 mallocs)
+  } else {
+    GSB_EV(ev, 1, st);
   }
+  GSB_EV(ev, 2, st);
   if (out->h_num_dup) *out->h_num_dup = D;
   if ((rc = bin_and_sort(ctx, N, D, out->depthg, cam.tiles_h, cam.tiles_w, nullptr, ctx->start.as<int32_t>(),
                          ctx->end.as<int32_t>(), st)))
     return rc;
+  GSB_EV(ev, 3, st);
   ctx->N = N; ctx->cam = cam; ctx->mode = is_sh ? PAY_SH : PAY_RGB; ctx->C = is_sh ? in->C : 1;
+  if (ctx->profiling) {
+    ctx->sum_dup += D;
+    if (!ctx->d_stats.p) {
+      if ((rc = ctx->d_stats.reserve(16))) return rc;
+      GSB_CUDA(cudaMemsetAsync(ctx->d_stats.p, 0, 16, st));
+    }
+  }
 
   CompositeArgs a;
   a.splat = ctx->splat.as<Splat>();
@@ -364,7 +397,10 @@ int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb
   a.write_empty = 1;
   a.out = out->rgb; a.T = out->T;
   a.depth = out->depth; a.opacity = out->opacity; a.z2 = out->z2;
-  return launch_composite_fwd(is_sh ? PAY_SH : PAY_RGB, is_sh ? in->C : 1, extras, a, st);
+  a.stats = ctx->profiling ? ctx->d_stats.as<unsigned long long>() : nullptr;
+  if ((rc = launch_composite_fwd(is_sh ? PAY_SH : PAY_RGB, is_sh ? in->C : 1, extras, a, st))) return rc;
+  GSB_EV(ev, 4, st);
+  return GSB200_OK;
 }
 
 int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb200_view_in* in,
@@ -387,6 +423,9 @@ int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* camin, const gs
   GSB_CHECK(!extras || (g->depth && g->opacity && g->z2), GSB200_ERR_INVALID,
             "render_backward: saved depth / opacity / z2 images are required with their gradients");
   if ((rc = ctx->ggeom.reserve((size_t)N * 32))) return rc;
+  gsb200_ctx::EvSet* ev = nullptr;
+  if (ctx->profiling && (rc = next_evset(&ctx->bwd_sets, &ctx->bwd_cap, &ctx->bwd_used, &ev))) return rc;
+  GSB_EV(ev, 0, st);
   GSB_CUDA(cudaMemsetAsync(ctx->ggeom.p, 0, (size_t)N * 32, st));
   if (!is_sh) {
     if ((rc = ctx->gpay.reserve((size_t)N * 16))) return rc;
@@ -416,9 +455,49 @@ int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* camin, const gs
   if (ctx->D > 0 || g->g_bg) {
     if ((rc = launch_composite_bwd(is_sh ? PAY_SH : PAY_RGB, is_sh ? in->C : 1, extras, true, a, st))) return rc;
   }
-  return launch_project_bwd_fused(N, in->mean, in->qvec, in->svec, g->mask, cam, ctx->ggeom.as<float4>(),
+  GSB_EV(ev, 1, st);
+  rc = launch_project_bwd_fused(N, in->mean, in->qvec, in->svec, g->mask, cam, ctx->ggeom.as<float4>(),
                                   is_sh ? nullptr : ctx->gpay.as<float4>(), g->g_mean, g->g_qvec, g->g_svec,
                                   g->g_alpha, is_sh ? nullptr : g->g_color, g->g_mean2d, st);
+  if (rc) return rc;
+  GSB_EV(ev, 2, st);
+  return GSB200_OK;
+}
+
+int gsb200_ctx_set_profiling(gsb200_ctx* ctx, int enable) {
+  int rc;
+  if ((rc = set_device(ctx))) return rc;
+  ctx->profiling = enable ? 1 : 0;
+  return GSB200_OK;
+}
+
+int gsb200_ctx_get_profile(gsb200_ctx* ctx, float* h_ms, int64_t* h_counts, int reset) {
+  int rc;
+  if ((rc = set_device(ctx))) return rc;
+  GSB_CHECK(h_ms && h_counts, GSB200_ERR_INVALID, "null output");
+  GSB_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < 6; ++i) h_ms[i] = 0.f;
+  for (int i = 0; i < ctx->fwd_used; ++i)
+    for (int k = 0; k < 4; ++k) {
+      float ms = 0.f;
+      GSB_CUDA(cudaEventElapsedTime(&ms, ctx->fwd_sets[i].e[k], ctx->fwd_sets[i].e[k + 1]));
+      h_ms[k] += ms;
+    }
+  for (int i = 0; i < ctx->bwd_used; ++i)
+    for (int k = 0; k < 2; ++k) {
+      float ms = 0.f;
+      GSB_CUDA(cudaEventElapsedTime(&ms, ctx->bwd_sets[i].e[k], ctx->bwd_sets[i].e[k + 1]));
+      h_ms[4 + k] += ms;
+    }
+  unsigned long long st2[2] = {0, 0};
+  if (ctx->d_stats.p) GSB_CUDA(cudaMemcpy(st2, ctx->d_stats.p, 16, cudaMemcpyDeviceToHost));
+  h_counts[0] = ctx->fwd_used; h_counts[1] = ctx->bwd_used; h_counts[2] = ctx->sum_dup;
+  h_counts[3] = (int64_t)st2[0]; h_counts[4] = (int64_t)st2[1];
+  if (reset) {
+    ctx->fwd_used = 0; ctx->bwd_used = 0; ctx->sum_dup = 0;
+    if (ctx->d_stats.p) GSB_CUDA(cudaMemset(ctx->d_stats.p, 0, 16));
+  }
+  return GSB200_OK;
 }
 
 int gsb200_view_stats(gsb200_ctx* ctx, int64_t* h_out, gsb200_stream stream) {

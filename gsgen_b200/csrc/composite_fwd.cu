@@ -23,6 +23,7 @@ k_composite_fwd(const CompositeArgs a) {
   constexpr int CC = PT::CC;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t s_bar[2];
+  __shared__ int s_reach;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y;
@@ -63,10 +64,12 @@ k_composite_fwd(const CompositeArgs a) {
     mbar_init(&s_bar[1], 1);
     fence_mbar_init();
   }
+  if (tid == 0) s_reach = 0;
   __syncthreads();
 
   // per-pixel registers
   float T = 1.0f;
+  int reach = 0, staged = 0;  // statistics only (a.stats)
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;          // rgb / scalar in acc0
   float accD = 0.f, accO = 0.f, accZ = 0.f;          // extras
   bool done = !pg.inside || (1.0f < a.thresh);
@@ -89,6 +92,7 @@ k_composite_fwd(const CompositeArgs a) {
     if (PAY == PAY_SH && use_bulk && tid == 0) mbar_arrive_expect_tx(&s_bar[0], (uint32_t)cnt0 * 3 * CC * 4);
     if (tid < B) stage_entry<PAY, C, B, false>(a, smem, tid, id0, tid < cnt0, use_bulk, &s_bar[0]);
     else cp_async_commit();
+    staged = cnt0;
   }
   int id_next = 0;
   if (nb > 1) { int j = B + tid; id_next = (tid < B && j < n) ? ids[j] : 0; }
@@ -105,6 +109,7 @@ k_composite_fwd(const CompositeArgs a) {
       if (tid < B) stage_entry<PAY, C, B, false>(a, smem + ((b + 1) & 1) * L::kBytes, tid, id_next, tid < cntn,
                                                  use_bulk, barn);
       else cp_async_commit();
+      staged += cntn;
       if (b + 2 < nb) { int j = (b + 2) * B + tid; id_next = (tid < B && j < n) ? ids[j] : 0; }
       cp_async_wait<1>();
     } else {
@@ -166,6 +171,7 @@ k_composite_fwd(const CompositeArgs a) {
           if (ok) {
             T = fmaf(-aG, T, T);           // T *= (1 - a*G)
             done = T < a.thresh;           // reference tests T < thresh before the NEXT Gaussian
+            if (done) reach = b * B + jj + 1;
           }
         }
         if (__all_sync(kFull, done)) { warp_done = true; break; }
@@ -181,6 +187,15 @@ k_composite_fwd(const CompositeArgs a) {
     }
   }
 
+  if (a.stats) {  // D_eff bookkeeping for the roofline report; not on the default path
+    const int r = pg.inside ? (done ? reach : n) : 0;
+    atomicMax(&s_reach, r);
+    __syncthreads();
+    if (tid == 0) {
+      atomicAdd(a.stats, (unsigned long long)s_reach);
+      atomicAdd(a.stats + 1, (unsigned long long)staged);
+    }
+  }
   if (!pg.inside) return;
   if constexpr (PAY == PAY_SH) {
     if (a.bg_rgb) {  // vol_render_bg.h:102-104

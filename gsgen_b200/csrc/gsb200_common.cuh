@@ -82,6 +82,13 @@ struct gsb200_ctx {
   int sorted_sel = 0;          // which vals[] holds the sorted ids
   gsb::Camera cam;
   int mode = 0, C = 0;
+  // stage profiling (bench only)
+  int profiling = 0;
+  struct EvSet { cudaEvent_t e[5]; };
+  EvSet* fwd_sets = nullptr; int fwd_cap = 0, fwd_used = 0;
+  EvSet* bwd_sets = nullptr; int bwd_cap = 0, bwd_used = 0;
+  gsb::Buf d_stats;            // unsigned long long[2]: D_eff, staged
+  int64_t sum_dup = 0;
 };
 
 namespace gsb {

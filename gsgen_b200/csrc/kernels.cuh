@@ -48,6 +48,9 @@ struct CompositeArgs {
   float* ggeom = nullptr;              // [N,8] fused gradient record (replaces grad_mean/cov/alpha)
   float* gpay = nullptr;               // [N,4] fused colour gradient record
   float* g_bg = nullptr;               // [H,W,3] or nullptr
+  // optional counters (profiling only): [0] += D_eff of the tile (1 + last list index any pixel needed),
+  // [1] += list entries actually staged into shared memory
+  unsigned long long* stats = nullptr;
 };
 
 // preprocess.cu

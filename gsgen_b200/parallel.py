@@ -1,0 +1,96 @@
+"""Multi-GPU data parallelism over VIEWS -- new work, the reference is single-GPU
+(its batch loop renders views sequentially: gs/gaussian_splatting.py:1439-1460; the per-view parameter
+gradients are summed by autograd before one optimizer.step(), trainer.py:587-599).
+
+One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  Every rank holds all Gaussian
+parameters; rank r renders the views {v : v mod G == r}; gradients accumulate locally into ONE flat fp32
+buffer (the parameter .grad tensors are views of it, so there is no pack pass) and a single
+`all_reduce(SUM)` per step makes the replicas identical -- 11+3*C*C floats per Gaussian (236 B at SH
+degree 3).  SUM (not AVG) reproduces the single-GPU gradient of the same view batch, which is what the
+renderer-level contract is; a trainer that normalises its loss by the local batch must divide by the
+global batch instead (guidance/stable_diffusion.py:304).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+FIELDS_RGB = (("mean", 3), ("qvec", 4), ("svec", 3), ("alpha", 1), ("color", 3))
+
+
+def field_layout(N: int, C: Optional[int]) -> List[tuple]:
+    """[(name, shape, offset, numel)] of the flat buffers.  C=None -> RGB colour, else SH [N,3,C*C]."""
+    fields = [("mean", (N, 3)), ("qvec", (N, 4)), ("svec", (N, 3)), ("alpha", (N,))]
+    fields.append(("color", (N, 3)) if C is None else ("sh", (N, 3, C * C)))
+    out, off = [], 0
+    for name, shape in fields:
+        n = 1
+        for s in shape:
+            n *= s
+        out.append((name, shape, off, n))
+        off += n
+    return out
+
+
+def shard_views(n_views: int, rank: int, world: int) -> List[int]:
+    """Round-robin view assignment: 1 view/GPU when n_views == world (BASELINE config 4 at 8 GPUs)."""
+    return [v for v in range(n_views) if v % world == rank]
+
+
+class ViewParallelRenderer:
+    """Replicated Gaussians + view-sharded rendering + one flat gradient all-reduce per step.
+
+    render_fn(params: dict of leaf tensors, view_index) -> loss-like scalar or (tensor, grad) pair;
+    the default (GPU) implementation is `gsgen_b200.rasterizer.render_view`.  The hook exists so that the
+    host-side logic (layout, sharding, collective) is testable on CPU with gloo.
+    """
+
+    def __init__(self, params: Dict[str, torch.Tensor], C: Optional[int], device, group=None):
+        self.C = C
+        self.device = torch.device(device)
+        self.group = group
+        N = params["mean"].shape[0]
+        self.N = N
+        self.layout = field_layout(N, C)
+        total = self.layout[-1][2] + self.layout[-1][3]
+        self.flat_param = torch.empty(total, dtype=torch.float32, device=self.device)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.params: Dict[str, torch.Tensor] = {}
+        self.grad_views: Dict[str, torch.Tensor] = {}
+        for name, shape, off, n in self.layout:
+            self.flat_param[off:off + n].copy_(params[name].reshape(-1).to(self.device, torch.float32))
+            p = self.flat_param[off:off + n].view(shape)
+            p.requires_grad_(True)
+            self.params[name] = p
+            self.grad_views[name] = self.flat_grad[off:off + n].view(shape)
+
+    @property
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    @property
+    def rank(self) -> int:
+        return dist.get_rank(self.group) if dist.is_available() and dist.is_initialized() else 0
+
+    def grad_bytes(self) -> int:
+        return self.flat_grad.numel() * 4
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+        for name, p in self.params.items():
+            p.grad = self.grad_views[name]  # autograd accumulates in place into the flat buffer
+
+    def all_reduce(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+
+    def step(self, n_views: int, render_and_backward: Callable[[Dict[str, torch.Tensor], int], None]):
+        """zero grads -> local views fwd+bwd (gradients accumulate) -> one all-reduce.  Returns local view ids."""
+        self.zero_grad()
+        mine = shard_views(n_views, self.rank, self.world)
+        for v in mine:
+            render_and_backward(self.params, v)
+        self.all_reduce()
+        return mine

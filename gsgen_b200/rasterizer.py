@@ -25,7 +25,7 @@ def make_camera_struct(c2w: torch.Tensor, camera_info, *, frustum_radius=6.0, ti
                        skip_frustum_culling=False, depth_detach=True) -> Gsb200Camera:
     """Host-side view description.  The frustum planes come from `CameraInfo.get_frustum`
     (utils/camera.py:260-294) evaluated on the CPU copy of c2w."""
-    h = c2w.detach().to("cpu", torch.float32)[:3, :4].contiguous()
+    h = c2w.detach().to("cpu", torch.float32)[:3, :4].contiguous()  # a CUDA c2w costs one D2H sync: pass the host pose
     cam = Gsb200Camera()
     cam.c2w = (ctypes.c_float * 12)(*h.view(-1).tolist())
     cam.fx, cam.fy, cam.cx, cam.cy = camera_info.fx, camera_info.fy, camera_info.cx, camera_info.cy

@@ -225,6 +225,17 @@ typedef struct gsb200_view_grads {
 int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* cam, const gsb200_view_in* in,
                            const gsb200_view_grads* g, gsb200_stream stream);
 
+/* Stage timing for the roofline report: when enabled, render_forward / render_backward bracket their stages
+ * with CUDA events on the caller's stream (no extra synchronisation inside the timed region).
+ * gsb200_ctx_get_profile synchronises the device and returns the sums since the last reset:
+ *   h_ms[0] cull+project+AABB+count   h_ms[1] scan + count read-back   h_ms[2] key emit + radix sort + ranges
+ *   h_ms[3] composite forward         h_ms[4] gradient memset + composite backward
+ *   h_ms[5] projection backward
+ *   h_counts[0] forward calls  [1] backward calls  [2] sum N_with_dub  [3] sum D_eff (1 + last list index any
+ *   pixel of a tile needed)  [4] sum list entries staged into shared memory by the forward */
+int gsb200_ctx_set_profiling(gsb200_ctx* ctx, int enable);
+int gsb200_ctx_get_profile(gsb200_ctx* ctx, float* h_ms /*[6]*/, int64_t* h_counts /*[5]*/, int reset);
+
 /* per-view statistics of the last forward on ctx (synchronises): h_out[0]=N_with_dub,
  * h_out[1]=number of Gaussians passing the frustum test, h_out[2]=max tile list length */
 int gsb200_view_stats(gsb200_ctx* ctx, int64_t* h_out, gsb200_stream stream);

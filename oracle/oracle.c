@@ -125,7 +125,9 @@ static inline float gauss2d_f32(const float *mean, const float *cov, const float
   /* reference: (float)expf(-0.5 * radial): -0.5 is a double literal -> product in double */
   return (float)expf((float)(-0.5 * (double)radial));
 }
-/* kernels.h:394-418 kernel_gaussian_2d_backward (fp64 inverse), accumulates into double sinks */
+/* kernels.h:394-418 kernel_gaussian_2d_backward (fp64 inverse).  The reference adds into shared memory with
+ * float atomics and then into global memory; here each tile accumulates its list in thread-private fp64 sinks
+ * (loc_* arrays indexed by list position) that are flushed once per (tile, Gaussian) instance. */
 static inline void gauss2d_bwd_f64(const float *mean, const float *cov, const float *q, float grad,
                                    double *gmean, double *gcov) {
   double d_grad = (double)grad;
@@ -135,12 +137,12 @@ static inline void gauss2d_bwd_f64(const float *mean, const float *cov, const fl
   double y = q[1] - mean[1];
   double tx = (x * c3 - y * c2) / det;
   double ty = (-x * c1 + y * c0) / det;
-  ATOMIC_ADD(gmean[0], (double)(float)(d_grad * tx));
-  ATOMIC_ADD(gmean[1], (double)(float)(d_grad * ty));
-  ATOMIC_ADD(gcov[0], (double)(float)(0.5 * (float)(d_grad * tx * tx)));
-  ATOMIC_ADD(gcov[1], (double)(float)(0.5 * (float)(d_grad * tx * ty)));
-  ATOMIC_ADD(gcov[2], (double)(float)(0.5 * (float)(d_grad * ty * tx)));
-  ATOMIC_ADD(gcov[3], (double)(float)(0.5 * (float)(d_grad * ty * ty)));
+  gmean[0] += (double)(float)(d_grad * tx);
+  gmean[1] += (double)(float)(d_grad * ty);
+  gcov[0] += (double)(float)(0.5 * (float)(d_grad * tx * tx));
+  gcov[1] += (double)(float)(0.5 * (float)(d_grad * tx * ty));
+  gcov[2] += (double)(float)(0.5 * (float)(d_grad * ty * tx));
+  gcov[3] += (double)(float)(0.5 * (float)(d_grad * ty * ty));
 }
 
 /* per-view statistics the measurement plan needs */
@@ -233,6 +235,7 @@ void orc_composite_rgb_bwd(int N, const float *mean, const float *cov, const flo
     int n = end[tile] - s;
     if (n == 0) continue;
     int ty = tile / n_tiles_w, tx = tile % n_tiles_w;
+    double *loc = (double *)calloc((size_t)n * 10, 8); /* [n][2 mean | 4 cov | 3 colour | 1 alpha] */
     for (int ly = 0; ly < TILE; ++ly)
       for (int lx = 0; lx < TILE; ++lx) {
         int gy = ty * TILE + ly, gx = tx * TILE + lx;
@@ -251,19 +254,29 @@ void orc_composite_rgb_bwd(int N, const float *mean, const float *cov, const flo
           ctt[0] += color[3 * g + 0] * coeff;
           ctt[1] += color[3 * g + 1] * coeff;
           ctt[2] += color[3 * g + 2] * coeff;
-          ATOMIC_ADD(dcol[3 * g + 0], (double)(coeff * go[0]));
-          ATOMIC_ADD(dcol[3 * g + 1], (double)(coeff * go[1]));
-          ATOMIC_ADD(dcol[3 * g + 2], (double)(coeff * go[2]));
+          loc[10 * i + 6] += (double)(coeff * go[0]);
+          loc[10 * i + 7] += (double)(coeff * go[1]);
+          loc[10 * i + 8] += (double)(coeff * go[2]);
           double partial_aG = 0.0;
           for (int j = 0; j < 3; ++j)
             partial_aG += (double)((color[3 * g + j] * cum - (fin[j] - ctt[j]) / (1 - a * G)) * go[j]);
           /* third arg is float in the reference signature: (float)(partial_aG * alpha_ * G) */
-          gauss2d_bwd_f64(mean + 2 * g, cov + 4 * g, pos, (float)(partial_aG * a * G), dm + 2 * g,
-                          dc + 4 * g);
-          ATOMIC_ADD(da[g], (double)(float)(partial_aG * G));
+          gauss2d_bwd_f64(mean + 2 * g, cov + 4 * g, pos, (float)(partial_aG * a * G), loc + 10 * i,
+                          loc + 10 * i + 2);
+          loc[10 * i + 9] += (double)(float)(partial_aG * G);
           cum *= (1 - a * G);
         }
       }
+    for (int i = 0; i < n; ++i) {
+      int g = ids[s + i];
+      const double *l = loc + 10 * i;
+      if (l[0] == 0.0 && l[1] == 0.0 && l[6] == 0.0 && l[7] == 0.0 && l[8] == 0.0 && l[9] == 0.0) continue;
+      ATOMIC_ADD(dm[2 * g], l[0]); ATOMIC_ADD(dm[2 * g + 1], l[1]);
+      for (int k = 0; k < 4; ++k) ATOMIC_ADD(dc[4 * g + k], l[2 + k]);
+      for (int k = 0; k < 3; ++k) ATOMIC_ADD(dcol[3 * g + k], l[6 + k]);
+      ATOMIC_ADD(da[g], l[9]);
+    }
+    free(loc);
   }
   for (int i = 0; i < N * 2; ++i) gmean[i] += (float)dm[i];
   for (int i = 0; i < N * 4; ++i) gcov[i] += (float)dc[i];
@@ -326,6 +339,7 @@ void orc_composite_scalar_bwd(int N, const float *mean, const float *cov, const 
     int n = end[tile] - s;
     if (n == 0) continue;
     int ty = tile / n_tiles_w, tx = tile % n_tiles_w;
+    double *loc = (double *)calloc((size_t)n * 8, 8); /* [n][2 mean | 4 cov | 1 scalar | 1 alpha] */
     for (int ly = 0; ly < TILE; ++ly)
       for (int lx = 0; lx < TILE; ++lx) {
         int gy = ty * TILE + ly, gx = tx * TILE + lx;
@@ -341,14 +355,24 @@ void orc_composite_scalar_bwd(int N, const float *mean, const float *cov, const 
           if (a * G < MIN_RENDER_ALPHA) continue;
           float coeff = a * cum * G;
           o += scalar[g] * coeff;
-          ATOMIC_ADD(ds[g], (double)(coeff * go));
+          loc[8 * i + 6] += (double)(coeff * go);
           float partial_aG = 0.0f;
           partial_aG += go * (scalar[g] * cum - (fin - o) / (1 - a * G));
-          gauss2d_bwd_f64(mean + 2 * g, cov + 4 * g, pos, partial_aG * a * G, dm + 2 * g, dc + 4 * g);
-          ATOMIC_ADD(da[g], (double)(partial_aG * G));
+          gauss2d_bwd_f64(mean + 2 * g, cov + 4 * g, pos, partial_aG * a * G, loc + 8 * i, loc + 8 * i + 2);
+          loc[8 * i + 7] += (double)(partial_aG * G);
           cum *= (1 - a * G);
         }
       }
+    for (int i = 0; i < n; ++i) {
+      int g = ids[s + i];
+      const double *l = loc + 8 * i;
+      if (l[0] == 0.0 && l[1] == 0.0 && l[6] == 0.0 && l[7] == 0.0) continue;
+      ATOMIC_ADD(dm[2 * g], l[0]); ATOMIC_ADD(dm[2 * g + 1], l[1]);
+      for (int k = 0; k < 4; ++k) ATOMIC_ADD(dc[4 * g + k], l[2 + k]);
+      ATOMIC_ADD(ds[g], l[6]);
+      ATOMIC_ADD(da[g], l[7]);
+    }
+    free(loc);
   }
   for (int i = 0; i < N * 2; ++i) gmean[i] += (float)dm[i];
   for (int i = 0; i < N * 4; ++i) gcov[i] += (float)dc[i];
@@ -486,6 +510,8 @@ void orc_composite_sh_bwd(int N, const float *mean, const float *cov, const floa
     int n = end[tile] - s;
     if (n == 0) continue;
     int ty = tile / n_tiles_w, tx = tile % n_tiles_w;
+    const int LK = 7 + 3 * CC; /* [n][2 mean | 4 cov | 1 alpha | 3*CC sh] */
+    double *loc = (double *)calloc((size_t)n * LK, 8);
     for (int ly = 0; ly < TILE; ++ly)
       for (int lx = 0; lx < TILE; ++lx) {
         int gy = ty * TILE + ly, gx = tx * TILE + lx;
@@ -513,17 +539,29 @@ void orc_composite_sh_bwd(int N, const float *mean, const float *cov, const floa
           for (int c = 0; c < 3; ++c) o[c] += coeff * y[c];
           for (int c = 0; c < 3; ++c) {
             float gr = coeff * (y[c] * (1.0f - y[c])) * go[c];
-            double *dst = dsh + (size_t)(3 * g + c) * CC;
-            for (int k = 0; k < CC; ++k) ATOMIC_ADD(dst[k], (double)(gr * Y[k]));
+            double *dst = loc + (size_t)LK * i + 7 + c * CC;
+            for (int k = 0; k < CC; ++k) dst[k] += (double)(gr * Y[k]);
           }
           float partial_aG = 0.0f;
           for (int c = 0; c < 3; ++c)
             partial_aG += go[c] * (y[c] * cum - (fin[c] - o[c]) / (1 - a * G));
-          gauss2d_bwd_f64(mean + 2 * g, cov + 4 * g, pos, partial_aG * a * G, dm + 2 * g, dc + 4 * g);
-          ATOMIC_ADD(da[g], (double)(partial_aG * G));
+          gauss2d_bwd_f64(mean + 2 * g, cov + 4 * g, pos, partial_aG * a * G, loc + (size_t)LK * i, loc + (size_t)LK * i + 2);
+          loc[(size_t)LK * i + 6] += (double)(partial_aG * G);
           cum *= (1 - a * G);
         }
       }
+    for (int i = 0; i < n; ++i) {
+      int g = ids[s + i];
+      const double *l = loc + (size_t)LK * i;
+      int any = 0;
+      for (int k = 0; k < LK; ++k) any |= (l[k] != 0.0);
+      if (!any) continue;
+      ATOMIC_ADD(dm[2 * g], l[0]); ATOMIC_ADD(dm[2 * g + 1], l[1]);
+      for (int k = 0; k < 4; ++k) ATOMIC_ADD(dc[4 * g + k], l[2 + k]);
+      ATOMIC_ADD(da[g], l[6]);
+      for (int k = 0; k < 3 * CC; ++k) ATOMIC_ADD(dsh[(size_t)g * 3 * CC + k], l[7 + k]);
+    }
+    free(loc);
   }
   for (int i = 0; i < N * 2; ++i) gmean[i] += (float)dm[i];
   for (int i = 0; i < N * 4; ++i) gcov[i] += (float)dc[i];

@@ -1,0 +1,179 @@
+"""-m gpu parity tests of the fused path (gsb200_render_forward / _backward through
+gsgen_b200.rasterizer.render_view) against the CPU oracle's restatement of the whole view
+(render_one / SHRenderer.forward): images, by-products and the gradients of mean / qvec / svec / alpha /
+color | sh (the BASELINE north_star's "grads for xyz/scale/rot/opacity/SH")."""
+import pytest
+import torch
+
+from gsgen_b200.scenes import make_scene
+from tests.util import assert_grad_close, assert_image_close, ocam_of
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _leaves(sc, dev):
+    mk = lambda t: t.to(dev).clone().requires_grad_()
+    return mk(sc.mean), mk(sc.qvec), mk(sc.svec), mk(sc.alpha)
+
+
+def _margin(oracle, aux, color_or_none, alpha_masked):
+    """threshold margin map of the view from the oracle (RGB forward on the same lists)."""
+    col = color_or_none if color_or_none is not None else torch.zeros(aux["mean2d"].shape[0], 3)
+    _, _, _, margin = oracle.composite_rgb_fwd(aux["mean2d"].detach().contiguous(), aux["cov2d"].detach().contiguous(),
+                                               col.contiguous(), alpha_masked.contiguous(), aux["start"], aux["end"],
+                                               aux["ids"], aux["topleft"], aux["cfg"], want_margin=True)
+    return margin
+
+
+@pytest.mark.parametrize("cfg", ["c1", "dense"])
+def test_fused_rgb_view(oracle_mod, cfg):
+    from gsgen_b200.rasterizer import render_view
+
+    if cfg == "c1":
+        sc = make_scene("c1", N=6000, reso=192)
+    else:
+        sc = make_scene("c3", N=8000, reso=176)
+        sc.svec = (sc.svec * 4.0).contiguous()
+    cam, c2w = sc.cams[0], sc.c2ws[0]
+    H, W = cam.h, cam.w
+    g = torch.Generator().manual_seed(5)
+    bg = torch.rand(H, W, 3, generator=g)
+    w_rgb, w_d = torch.randn(H, W, 3, generator=g), torch.randn(H, W, 1, generator=g)
+    w_o, w_z = torch.randn(H, W, 1, generator=g), torch.randn(H, W, 1, generator=g)
+
+    # oracle (CPU, autograd through the restated torch ops + C composites)
+    mo, qo, so, ao = _leaves(sc, "cpu")
+    co = sc.color.clone().requires_grad_()
+    bgo = bg.clone().requires_grad_()
+    ref = oracle_mod.render_view(mo, qo, so, ao, c2w, ocam_of(cam), color=co, bg=bgo, rgb_only=False)
+    loss = (ref["rgb"] * w_rgb).sum() + (ref["depth"] * w_d).sum() + (ref["opacity"] * w_o).sum() + \
+        (ref["z_var"] * w_z).sum()
+    loss.backward()
+    aux = ref["aux"]
+    margin = _margin(oracle_mod, aux, sc.color[aux["mask"]], sc.alpha[aux["mask"]])
+
+    # ours
+    mg, qg, sg, ag = _leaves(sc, DEV)
+    cg = sc.color.to(DEV).clone().requires_grad_()
+    bgg = bg.to(DEV).clone().requires_grad_()
+    out = render_view(mg, qg, sg, ag, c2w.to(DEV), cam, color=cg, bg=bgg, rgb_only=False)
+    d = lambda t: t.to(DEV)
+    loss = (out["rgb"] * d(w_rgb)).sum() + (out["depth"] * d(w_d)).sum() + (out["opacity"] * d(w_o)).sum() + \
+        (out["z_var"] * d(w_z)).sum()
+    loss.backward()
+
+    a = out["aux"]
+    assert torch.equal(a["mask"].cpu(), aux["mask"])
+    assert a["N_with_dub"] == aux["D"], (a["N_with_dub"], aux["D"])
+    mk = aux["mask"]
+    assert torch.allclose(a["mean2d"].detach().cpu()[mk], aux["mean2d"].detach(), rtol=2e-5, atol=1e-6)
+    assert torch.allclose(a["depth"].cpu()[mk], aux["depth"].detach(), rtol=2e-6, atol=1e-6)
+    assert_image_close(out["rgb"], ref["rgb"], margin, what="rgb", atol=2e-4)
+    assert_image_close(out["opacity"].squeeze(-1), ref["opacity"].squeeze(-1), margin, what="opacity", atol=2e-4)
+    zs = max(1.0, float(ref["depth"].abs().max()))
+    assert_image_close(out["depth"].squeeze(-1) / zs, ref["depth"].squeeze(-1) / zs, margin, what="depth", atol=2e-4)
+    assert_image_close(out["z_var"].squeeze(-1) / zs ** 2, ref["z_var"].squeeze(-1) / zs ** 2, margin, what="z_var",
+                       atol=5e-4)
+    # opacity + T == 1 (size-independent identity of the blend)
+    assert float((out["opacity"] + out["T"] - 1).abs().max()) < 2e-5
+    tol = 3e-3  # end-to-end: projection differences + flips feed the 1e-3 per-op tolerance
+    assert_grad_close(mg.grad, mo.grad, tol, "g_mean")
+    assert_grad_close(qg.grad, qo.grad, tol, "g_qvec")
+    assert_grad_close(sg.grad, so.grad, tol, "g_svec")
+    assert_grad_close(ag.grad, ao.grad, tol, "g_alpha")
+    assert_grad_close(cg.grad, co.grad, tol, "g_color")
+    assert_image_close(bgg.grad, bgo.grad, margin, what="g_bg", atol=5e-4)
+    # densification statistic: gradient w.r.t. the projected mean (gaussian_splatting.py:464-469)
+    assert_grad_close(a["mean2d_grad"].cpu()[mk], aux["mean2d"].grad, tol, "g_mean2d")
+    assert float(a["mean2d_grad"].cpu()[~mk].abs().max() if (~mk).any() else 0.0) == 0.0
+    # radii2d by-product (gaussian_splatting.py:1240-1245)
+    cov = aux["cov2d"].detach()
+    m = (cov[:, 0, 0] + cov[:, 1, 1]) / 2
+    r_ref = m + torch.sqrt((m ** 2 - torch.det(cov)).clamp(min=0))
+    assert torch.allclose(a["radii2d"].cpu()[mk], r_ref, rtol=1e-3, atol=1e-9)
+
+
+@pytest.mark.parametrize("C,with_bg", [(1, False), (3, True), (4, False)])
+def test_fused_sh_view(oracle_mod, C, with_bg):
+    from gsgen_b200.rasterizer import render_view
+
+    sc = make_scene("c3", N=6000, reso=160)
+    sc.svec = (sc.svec * 3.0).contiguous()
+    cam, c2w = sc.cams[0], sc.c2ws[0]
+    H, W = cam.h, cam.w
+    g = torch.Generator().manual_seed(9 + C)
+    sh_full = (0.5 * torch.randn(sc.N, 3, C * C, generator=g)).contiguous()
+    w_rgb = torch.randn(H, W, 3, generator=g)
+    bg_rgb = torch.tensor([0.3, 0.1, 0.6]) if with_bg else None
+
+    mo, qo, so, ao = _leaves(sc, "cpu")
+    sho = sh_full.clone().requires_grad_()
+    ref = oracle_mod.render_view(mo, qo, so, ao, c2w, ocam_of(cam), sh=sho, C=C, bg_rgb=bg_rgb)
+    (ref["rgb"] * w_rgb).sum().backward()
+    aux = ref["aux"]
+    margin = _margin(oracle_mod, aux, None, sc.alpha[aux["mask"]])
+
+    mg, qg, sg, ag = _leaves(sc, DEV)
+    shg = sh_full.to(DEV).clone().requires_grad_()
+    out = render_view(mg, qg, sg, ag, c2w.to(DEV), cam, sh=shg, C=C,
+                      bg_rgb=None if bg_rgb is None else bg_rgb.to(DEV))
+    (out["rgb"] * w_rgb.to(DEV)).sum().backward()
+    assert torch.equal(out["aux"]["mask"].cpu(), aux["mask"])
+    assert out["aux"]["N_with_dub"] == aux["D"]
+    assert_image_close(out["rgb"], ref["rgb"], margin, what=f"sh rgb C={C}", atol=2e-4)
+    tol = 3e-3
+    assert_grad_close(mg.grad, mo.grad, tol, "g_mean")
+    assert_grad_close(qg.grad, qo.grad, tol, "g_qvec")
+    assert_grad_close(sg.grad, so.grad, tol, "g_svec")
+    assert_grad_close(ag.grad, ao.grad, tol, "g_alpha")
+    assert_grad_close(shg.grad, sho.grad, tol, "g_sh")
+
+
+def test_fused_matches_compat_ops_exactly(oracle_mod):
+    """The fused path and the chain of reference-shaped ops run the same kernels: identical images when fed the
+    same projected Gaussians (deterministic forward)."""
+    from gsgen_b200.backend import _backend
+    from gsgen_b200.culling import tile_culling_aabb_count
+    from gsgen_b200.rasterizer import render_view
+
+    sc = make_scene("c1", N=5000, reso=160).to(DEV)
+    cam, c2w = sc.cams[0], sc.c2ws[0]
+    H, W = cam.h, cam.w
+    out = render_view(sc.mean, sc.qvec, sc.svec, sc.alpha, c2w, cam, color=sc.color, rgb_only=True)
+    a = out["aux"]
+    mask = a["mask"]
+    idx = torch.nonzero(mask).squeeze(1)
+    m2, c2, dp = a["mean2d"][idx].contiguous(), a["cov2d"][idx].contiguous(), a["depth"][idx].contiguous()
+    D, tl, br = tile_culling_aabb_count(m2, c2, 16, cam, 6.0)
+    assert D == a["N_with_dub"]
+    th, tw = cam.n_tiles
+    ids = torch.zeros(D, dtype=torch.int32, device=DEV)
+    start = -torch.ones(th * tw, dtype=torch.int32, device=DEV)
+    end = -torch.ones(th * tw, dtype=torch.int32, device=DEV)
+    _backend.tile_culling_aabb_start_end(tl, br, ids, start, end, dp, th, tw)
+    o = torch.zeros(H, W, 3, device=DEV)
+    T = torch.ones(H, W, 1, device=DEV)
+    topleft = torch.tensor([-cam.cx / cam.fx, -cam.cy / cam.fy], device=DEV)
+    _backend.tile_based_vol_rendering_start_end_with_T(m2, c2, sc.color[idx].contiguous(), sc.alpha[idx].contiguous(),
+                                                       start, end, ids, o, topleft, 16, th, tw, 1.0 / cam.fx,
+                                                       1.0 / cam.fy, H, W, 1e-4, T)
+    assert torch.allclose(o, out["rgb"], rtol=0, atol=1e-6)
+    assert torch.allclose(T, out["T"], rtol=0, atol=1e-6)
+
+
+def test_forward_is_deterministic_and_backward_stable():
+    from gsgen_b200.rasterizer import render_view
+
+    sc = make_scene("c3", N=20000, reso=256).to(DEV)
+    cam, c2w = sc.cams[0], sc.c2ws[0]
+    outs, grads = [], []
+    for _ in range(2):
+        sh = sc.sh.clone().requires_grad_()
+        o = render_view(sc.mean, sc.qvec, sc.svec, sc.alpha, c2w, cam, sh=sh, C=4,
+                        sh_c2w=c2w[:3, :3].contiguous())
+        o["rgb"].square().sum().backward()
+        outs.append(o["rgb"].detach().clone())
+        grads.append(sh.grad.clone())
+    assert torch.equal(outs[0], outs[1])  # forward: bit-identical
+    assert_grad_close(grads[0], grads[1], 1e-5, "run-to-run g_sh")  # float atomics: order noise only
