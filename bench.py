@@ -323,7 +323,7 @@ def run_ours(args):
     def render_and_backward(params, v):
         # the pose is host data (it comes from the data loader): passing the CPU tensor avoids a D2H sync
         out = render_view(params["mean"], params["qvec"], params["svec"], params["alpha"], c2ws_cpu[v], cams[v],
-                          sh=params["sh"], C=C, slot=slot_of[v])
+                          sh=params["sh"], C=C, slot=slot_of[v], grad_sink=vpr.grad_views)
         out["rgb"].backward(gradient=gouts[v])
         last["rgb"], last["aux"] = out["rgb"], out["aux"]
 
@@ -414,7 +414,7 @@ def run_ours(args):
                 d_gout.copy_(h_gout, non_blocking=True)
                 out = render_view(vpr.params["mean"], vpr.params["qvec"], vpr.params["svec"], vpr.params["alpha"],
                                   h_c2w if v == v0 else c2ws_cpu[v], cams[v], sh=vpr.params["sh"], C=C,
-                                  slot=slot_of[v])
+                                  slot=slot_of[v], grad_sink=vpr.grad_views)
                 out["rgb"].backward(gradient=d_gout)
                 h_rgb.copy_(out["rgb"].detach(), non_blocking=True)
             vpr.all_reduce()

@@ -67,6 +67,7 @@ class Gsb200ViewGrads(ctypes.Structure):
         ("mask", c_void),
         ("g_mean", c_void), ("g_qvec", c_void), ("g_svec", c_void), ("g_alpha", c_void),
         ("g_color", c_void), ("g_sh", c_void), ("g_mean2d", c_void), ("g_bg", c_void),
+        ("accumulate", c_i32),
     ]
 
 

@@ -121,9 +121,11 @@ int gsb200_ctx_destroy(gsb200_ctx* c) {
   if (!c) return GSB200_OK;
   cudaSetDevice(c->device);
   gsb::Buf* bufs[] = {&c->splat, &c->pay, &c->rect, &c->count, &c->incl, &c->ggeom, &c->gpay, &c->keys[0],
-                      &c->keys[1], &c->vals[0], &c->vals[1], &c->cub_tmp, &c->start, &c->end, &c->d_total};
+                      &c->keys[1], &c->vals[0], &c->vals[1], &c->cub_tmp, &c->start, &c->end, &c->d_total,
+                      &c->count_sorted, &c->dkeys[0], &c->dkeys[1], &c->perm[0], &c->perm[1], &c->d_stats};
   for (auto* b : bufs) b->release();
   if (c->h_total) cudaFreeHost(c->h_total);
+  if (c->ev_total) cudaEventDestroy(c->ev_total);
   delete c;
   return GSB200_OK;
 }
@@ -147,19 +149,22 @@ int gsb200_tile_culling_aabb_start_end(gsb200_ctx* ctx, const int32_t* tl, const
   if (N > 0) {
     GSB_CHECK(tl && br && depth, GSB200_ERR_INVALID, "tile_culling_aabb_start_end: null tensor");
     if ((rc = ctx->count.reserve((size_t)N * 4))) return rc;
-    if ((rc = ctx->incl.reserve((size_t)N * 4))) return rc;
     if ((rc = ctx->rect.reserve((size_t)N * 8))) return rc;
-    if ((rc = launch_count_from_aabb(N, tl, br, ctx->count.as<int32_t>(), ctx->rect.as<ushort4>(), st))) return rc;
-    if ((rc = scan_counts(ctx, N, st))) return rc;
+    if ((rc = begin_total(ctx, st))) return rc;
+    if ((rc = launch_count_from_aabb(N, tl, br, ctx->count.as<int32_t>(), ctx->rect.as<ushort4>(),
+                                     ctx->d_total.as<unsigned long long>(), st)))
+      return rc;
+    if ((rc = request_total(ctx, st))) return rc;
+    if ((rc = sort_depths_and_scan(ctx, N, depth, st))) return rc;
   }
   int64_t total = 0;
-  if (N > 0 && (rc = read_total(ctx, N, &total, st))) return rc;
+  if (N > 0 && (rc = wait_total(ctx, &total))) return rc;
   // the reference asserts size_h == N_with_dub on the host (aabb_culling.h:228)
   GSB_CHECK(total == (int64_t)D, GSB200_ERR_MISMATCH,
             "tile_culling_aabb_start_end: AABBs expand to %lld duplicates but gaussian_ids has %u entries",
             (long long)total, D);
   GSB_CHECK(D == 0 || gaussian_ids, GSB200_ERR_INVALID, "null gaussian_ids");
-  return bin_and_sort(ctx, N, (int64_t)D, depth, (int)th, (int)tw, gaussian_ids, start, end, st);
+  return bin_and_sort(ctx, N, (int64_t)D, (int)th, (int)tw, gaussian_ids, start, end, st);
 }
 
 int gsb200_tile_based_vol_rendering_start_end_with_T(
@@ -314,13 +319,12 @@ int gsb200_tile_culling_aabb_count(gsb200_ctx* ctx, const float* mean2d, const f
   if (N == 0) return GSB200_OK;
   GSB_CHECK(mean2d && cov2d && tl && br, GSB200_ERR_INVALID, "tile_culling_aabb_count: null tensor");
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rc = ctx->count.reserve((size_t)N * 4))) return rc;
-  if ((rc = ctx->incl.reserve((size_t)N * 4))) return rc;
+  if ((rc = begin_total(ctx, st))) return rc;
   if ((rc = launch_aabb_count(N, mean2d, cov2d, (int)tile_size, fx, fy, cx, cy, (int)W, (int)H, D, tl, br,
-                              ctx->count.as<int32_t>(), st)))
+                              ctx->d_total.as<unsigned long long>(), st)))
     return rc;
-  if ((rc = scan_counts(ctx, N, st))) return rc;
-  return read_total(ctx, N, h_total, st);
+  if ((rc = request_total(ctx, st))) return rc;
+  return wait_total(ctx, h_total);
 }
 
 // ---- Part 3 -------------------------------------------------------------------------------------------
@@ -354,21 +358,23 @@ int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb
     if (!is_sh && (rc = ctx->pay.reserve((size_t)N * 16))) return rc;
     if ((rc = ctx->rect.reserve((size_t)N * 8))) return rc;
     if ((rc = ctx->count.reserve((size_t)N * 4))) return rc;
-    if ((rc = ctx->incl.reserve((size_t)N * 4))) return rc;
+    if ((rc = begin_total(ctx, st))) return rc;
     if ((rc = launch_preprocess(N, in->mean, in->qvec, in->svec, in->alpha, is_sh ? nullptr : in->color, cam,
                                 out->mean2d, out->cov2d, out->depthg, out->mask, out->radii2d,
                                 ctx->splat.as<Splat>(), ctx->pay.as<float4>(), ctx->rect.as<ushort4>(),
-                                ctx->count.as<int32_t>(), st)))
+                                ctx->count.as<int32_t>(), ctx->d_total.as<unsigned long long>(), st)))
       return rc;
+    if ((rc = request_total(ctx, st))) return rc;
     GSB_EV(ev, 1, st);
-    if ((rc = scan_counts(ctx, N, st))) return rc;
-    if ((rc = read_total(ctx, N, &D, st))) return rc;  // the one host sync of the view (reference: two + 5 mallocs)
+    if ((rc = sort_depths_and_scan(ctx, N, out->depthg, st))) return rc;  // GPU keeps working ...
+    if ((rc = wait_total(ctx, &D))) return rc;  // ... while the host waits only for the 8-byte count (the one host
+                                                // wait of the view; the reference blocks twice + 5 cudaMalloc/Free)
   } else {
     GSB_EV(ev, 1, st);
   }
   GSB_EV(ev, 2, st);
   if (out->h_num_dup) *out->h_num_dup = D;
-  if ((rc = bin_and_sort(ctx, N, D, out->depthg, cam.tiles_h, cam.tiles_w, nullptr, ctx->start.as<int32_t>(),
+  if ((rc = bin_and_sort(ctx, N, D, cam.tiles_h, cam.tiles_w, nullptr, ctx->start.as<int32_t>(),
                          ctx->end.as<int32_t>(), st)))
     return rc;
   GSB_EV(ev, 3, st);
@@ -458,7 +464,7 @@ int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* camin, const gs
   GSB_EV(ev, 1, st);
   rc = launch_project_bwd_fused(N, in->mean, in->qvec, in->svec, g->mask, cam, ctx->ggeom.as<float4>(),
                                   is_sh ? nullptr : ctx->gpay.as<float4>(), g->g_mean, g->g_qvec, g->g_svec,
-                                  g->g_alpha, is_sh ? nullptr : g->g_color, g->g_mean2d, st);
+                                  g->g_alpha, is_sh ? nullptr : g->g_color, g->g_mean2d, g->accumulate, st);
   if (rc) return rc;
   GSB_EV(ev, 2, st);
   return GSB200_OK;

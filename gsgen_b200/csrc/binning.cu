@@ -1,10 +1,22 @@
-// binning.cu -- tile binning (reference gs/src/include/aabb_culling.h:15-103, :192-260):
-//   counts --cub::DeviceScan--> offsets --k_emit_keys--> (tile<<32 | depth_bits, id)
-//          --cub::DeviceRadixSort (bits [0, 32+ceil(log2 T)))--> sorted ids --k_tile_ranges--> start/end
-// Differences from the reference, none of which change the result: slots come from a prefix sum instead
-// of one contended global atomic (deterministic order, no memset of D keys), the sort skips the key bits
-// that are always zero, start/end are produced by one kernel, scratch comes from the context arena
-// instead of 5x cudaMalloc/cudaFree per call, and everything is enqueued on the caller's stream.
+// binning.cu -- tile binning (reference gs/src/include/aabb_culling.h:15-103, :192-260).
+//
+// The reference sorts D = N_with_dub (tile<<32 | depth_bits, id) pairs with one 64-bit cub::DeviceRadixSort
+// (8 passes over 12 B/pair).  An LSD radix sort may process its digits in any grouping as long as every pass is
+// stable, and the 32 depth bits do not depend on the tile -- so they are sorted ONCE PER GAUSSIAN (N items)
+// instead of once per duplicate (D ~ 5 N items):
+//
+//   1. cub::DeviceRadixSort (u32 depth bits -> Gaussian index), N items           [low 32 key bits]
+//   2. counts gathered in depth order -> cub::DeviceScan -> slot offsets
+//   3. k_emit_tiles: every Gaussian, in depth order, writes (tile id, Gaussian index) for its tile rectangle
+//   4. cub::DeviceRadixSort (tile id bits only, stable), D items                   [high key bits]
+//   5. k_tile_ranges: start/end per tile (-1 for empty tiles)
+//
+// Result: exactly the order of the reference's signed 64-bit sort (depth bits compare as unsigned inside a tile,
+// negative depths after positive ones), ties (equal tile and depth bits) in Gaussian-index order (the reference's
+// tie order is whatever its atomic slot allocation produced).  Traffic: 8 B x 4 passes x N + 6 B x 2 passes x D
+// instead of 12 B x 8 passes x D.  Slots come from a prefix sum (no contended global atomic, no memset of D keys),
+// scratch from the context arena (the reference does 5x cudaMalloc/cudaFree per call), everything on the
+// caller's stream.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -13,26 +25,42 @@
 
 namespace gsb {
 
-// One warp expands 32 consecutive Gaussians cooperatively: for each Gaussian with duplicates the 32
-// lanes write its (key, id) pairs to consecutive slots (coalesced 8 B / 4 B stores).
 __global__ void __launch_bounds__(256)
-k_emit_keys(uint32_t N, const int32_t* __restrict__ count, const int32_t* __restrict__ incl,
-            const ushort4* __restrict__ rect, const float* __restrict__ depth, int tiles_w,
-            uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
+k_depth_keys(uint32_t N, const float* __restrict__ depth, uint32_t* __restrict__ keys, int32_t* __restrict__ idx) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  keys[i] = __float_as_uint(depth[i]);
+  idx[i] = (int32_t)i;
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_counts(uint32_t N, const int32_t* __restrict__ perm, const int32_t* __restrict__ count,
+                int32_t* __restrict__ count_sorted) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  count_sorted[j] = count[perm[j]];
+}
+
+// One warp expands 32 consecutive Gaussians (in depth order) cooperatively: for each Gaussian with duplicates the
+// 32 lanes write its (tile, id) pairs to consecutive slots (coalesced stores).
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+k_emit_tiles(uint32_t N, const int32_t* __restrict__ perm, const int32_t* __restrict__ count_sorted,
+             const int32_t* __restrict__ incl_sorted, const ushort4* __restrict__ rect, int tiles_w,
+             KeyT* __restrict__ keys, int32_t* __restrict__ vals) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t base = warp_global * 32;
   if (base >= N) return;
-  const uint32_t i = base + lane;
-  int c = 0, off = 0;
-  uint32_t dbits = 0;
+  const uint32_t j = base + lane;
+  int c = 0, off = 0, gid = 0;
   ushort4 r = make_ushort4(0, 0, 0, 0);
-  if (i < N) {
-    c = count[i];
+  if (j < N) {
+    c = count_sorted[j];
     if (c > 0) {
-      off = incl[i] - c;
-      r = rect[i];
-      dbits = __float_as_uint(depth[i]);
+      off = incl_sorted[j] - c;
+      gid = perm[j];
+      r = rect[gid];
     }
   }
   uint32_t have = __ballot_sync(0xffffffffu, c > 0);
@@ -41,15 +69,14 @@ k_emit_keys(uint32_t N, const int32_t* __restrict__ count, const int32_t* __rest
     have &= have - 1;
     int cg = __shfl_sync(0xffffffffu, c, g);
     int og = __shfl_sync(0xffffffffu, off, g);
-    uint32_t dg = __shfl_sync(0xffffffffu, dbits, g);
+    int idg = __shfl_sync(0xffffffffu, gid, g);
     int x0 = __shfl_sync(0xffffffffu, (int)r.x, g), y0 = __shfl_sync(0xffffffffu, (int)r.y, g);
     int x1 = __shfl_sync(0xffffffffu, (int)r.z, g);
     int w = x1 - x0 + 1;
     for (int k = lane; k < cg; k += 32) {
       int ty = y0 + k / w, tx = x0 + k % w;
-      uint32_t tile = (uint32_t)(ty * tiles_w + tx);
-      keys[og + k] = ((uint64_t)tile << 32) | (uint64_t)dg;
-      vals[og + k] = (int32_t)(base + g);
+      keys[og + k] = (KeyT)(ty * tiles_w + tx);
+      vals[og + k] = idg;
     }
   }
 }
@@ -61,39 +88,34 @@ k_fill_i32(int32_t* p, int32_t v, uint32_t n) {
 }
 
 // aabb_culling.h:70-103 fill_start_aabb + fill_end_aabb in one pass
+template <typename KeyT>
 __global__ void __launch_bounds__(256)
-k_tile_ranges(int64_t D, const uint64_t* __restrict__ keys, int32_t* __restrict__ start, int32_t* __restrict__ end) {
+k_tile_ranges(int64_t D, const KeyT* __restrict__ keys, int32_t* __restrict__ start, int32_t* __restrict__ end) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= D) return;
-  uint32_t t = (uint32_t)(keys[s] >> 32);
-  if (s == 0 || (uint32_t)(keys[s - 1] >> 32) != t) start[t] = (int32_t)s;
-  if (s == D - 1 || (uint32_t)(keys[s + 1] >> 32) != t) end[t] = (int32_t)(s + 1);
+  uint32_t t = (uint32_t)keys[s];
+  if (s == 0 || (uint32_t)keys[s - 1] != t) start[t] = (int32_t)s;
+  if (s == D - 1 || (uint32_t)keys[s + 1] != t) end[t] = (int32_t)(s + 1);
 }
 
-__global__ void k_total_from_scan(uint32_t N, const int32_t* __restrict__ incl, int64_t* __restrict__ total) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) *total = N ? (int64_t)incl[N - 1] : 0;
-}
-
-int scan_counts(gsb200_ctx* ctx, uint32_t N, cudaStream_t st) {
-  if (N == 0) return GSB200_OK;
-  size_t bytes = 0;
-  GSB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, ctx->count.as<int32_t>(), ctx->incl.as<int32_t>(), (int)N, st));
-  int rc = ctx->cub_tmp.reserve(bytes);
+// ---- duplicate count read-back ----------------------------------------------------------------------
+// The per-Gaussian kernels add their block sums of `count` into ctx->d_total (zeroed by begin_total); the 8-byte
+// copy is enqueued right behind them and an event marks it, so the host learns D while the GPU is already
+// sorting depths.  (The reference blocks twice per view: gs/culling.py:33-35 .item(), aabb_culling.h:227.)
+int begin_total(gsb200_ctx* ctx, cudaStream_t st) {
+  int rc = ctx->d_total.reserve(sizeof(unsigned long long));
   if (rc) return rc;
-  GSB_CUDA(cub::DeviceScan::InclusiveSum(ctx->cub_tmp.p, bytes, ctx->count.as<int32_t>(), ctx->incl.as<int32_t>(),
-                                         (int)N, st));
+  GSB_CUDA(cudaMemsetAsync(ctx->d_total.p, 0, sizeof(unsigned long long), st));
   return GSB200_OK;
 }
-
-// reads the duplicate count back to the host (the reference does the same: gs/culling.py:33-35 .item() and
-// aabb_culling.h:227 cudaMemcpy).  One 8-byte D2H copy + stream sync per view.
-int read_total(gsb200_ctx* ctx, uint32_t N, int64_t* h_total, cudaStream_t st) {
-  int rc = ctx->d_total.reserve(sizeof(int64_t));
-  if (rc) return rc;
-  k_total_from_scan<<<1, 32, 0, st>>>(N, ctx->incl.as<int32_t>(), ctx->d_total.as<int64_t>());
-  GSB_LAUNCH_CHECK();
+int request_total(gsb200_ctx* ctx, cudaStream_t st) {
+  if (!ctx->ev_total) GSB_CUDA(cudaEventCreateWithFlags(&ctx->ev_total, cudaEventDisableTiming));
   GSB_CUDA(cudaMemcpyAsync(ctx->h_total, ctx->d_total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  GSB_CUDA(cudaStreamSynchronize(st));
+  GSB_CUDA(cudaEventRecord(ctx->ev_total, st));
+  return GSB200_OK;
+}
+int wait_total(gsb200_ctx* ctx, int64_t* h_total) {
+  GSB_CUDA(cudaEventSynchronize(ctx->ev_total));
   *h_total = *ctx->h_total;
   return GSB200_OK;
 }
@@ -104,10 +126,65 @@ static int bits_for(uint32_t n) {  // ceil(log2(n)) for n >= 1
   return b;
 }
 
-// count/incl/rect in ctx, depth from the caller.  Writes sorted ids to ids_out (or leaves them in
-// ctx->vals[ctx->sorted_sel] when ids_out == nullptr) and start/end.
-int bin_and_sort(gsb200_ctx* ctx, uint32_t N, int64_t D, const float* depth, int tiles_h, int tiles_w,
-                 int32_t* ids_out, int32_t* start, int32_t* end, cudaStream_t st) {
+// Stage 1+2 (independent of D): depth order of the Gaussians and their slot offsets.
+int sort_depths_and_scan(gsb200_ctx* ctx, uint32_t N, const float* depth, cudaStream_t st) {
+  if (N == 0) return GSB200_OK;
+  int rc;
+  if ((rc = ctx->dkeys[0].reserve((size_t)N * 4))) return rc;
+  if ((rc = ctx->dkeys[1].reserve((size_t)N * 4))) return rc;
+  if ((rc = ctx->perm[0].reserve((size_t)N * 4))) return rc;
+  if ((rc = ctx->perm[1].reserve((size_t)N * 4))) return rc;
+  if ((rc = ctx->count_sorted.reserve((size_t)N * 4))) return rc;
+  if ((rc = ctx->incl.reserve((size_t)N * 4))) return rc;
+  const unsigned blocks = (N + 255) / 256;
+  k_depth_keys<<<blocks, 256, 0, st>>>(N, depth, ctx->dkeys[0].as<uint32_t>(), ctx->perm[0].as<int32_t>());
+  GSB_LAUNCH_CHECK();
+  size_t b1 = 0, b2 = 0;
+  GSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b1, ctx->dkeys[0].as<uint32_t>(), ctx->dkeys[1].as<uint32_t>(),
+                                           ctx->perm[0].as<int32_t>(), ctx->perm[1].as<int32_t>(), (int)N, 0, 32, st));
+  GSB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, b2, ctx->count_sorted.as<int32_t>(), ctx->incl.as<int32_t>(),
+                                         (int)N, st));
+  if ((rc = ctx->cub_tmp.reserve(b1 > b2 ? b1 : b2))) return rc;
+  GSB_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, b1, ctx->dkeys[0].as<uint32_t>(),
+                                           ctx->dkeys[1].as<uint32_t>(), ctx->perm[0].as<int32_t>(),
+                                           ctx->perm[1].as<int32_t>(), (int)N, 0, 32, st));
+  k_gather_counts<<<blocks, 256, 0, st>>>(N, ctx->perm[1].as<int32_t>(), ctx->count.as<int32_t>(),
+                                          ctx->count_sorted.as<int32_t>());
+  GSB_LAUNCH_CHECK();
+  GSB_CUDA(cub::DeviceScan::InclusiveSum(ctx->cub_tmp.p, b2, ctx->count_sorted.as<int32_t>(),
+                                         ctx->incl.as<int32_t>(), (int)N, st));
+  return GSB200_OK;
+}
+
+template <typename KeyT>
+static int emit_sort_ranges(gsb200_ctx* ctx, uint32_t N, int64_t D, int tiles_w, uint32_t T, int32_t* ids_out,
+                            int32_t* start, int32_t* end, cudaStream_t st) {
+  KeyT* k0 = ctx->keys[0].as<KeyT>();
+  KeyT* k1 = ctx->keys[1].as<KeyT>();
+  int32_t* v0 = ctx->vals[0].as<int32_t>();
+  int32_t* v1 = ids_out ? ids_out : ctx->vals[1].as<int32_t>();
+  const uint32_t warps = (N + 31) / 32;
+  k_emit_tiles<KeyT><<<(warps * 32 + 255) / 256, 256, 0, st>>>(N, ctx->perm[1].as<int32_t>(),
+                                                              ctx->count_sorted.as<int32_t>(),
+                                                              ctx->incl.as<int32_t>(), ctx->rect.as<ushort4>(),
+                                                              tiles_w, k0, v0);
+  GSB_LAUNCH_CHECK();
+  const int end_bit = bits_for(T) < 1 ? 1 : bits_for(T);
+  size_t bytes = 0;
+  GSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0, k1, v0, v1, (int)D, 0, end_bit, st));
+  int rc;
+  if ((rc = ctx->cub_tmp.reserve(bytes))) return rc;
+  GSB_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, bytes, k0, k1, v0, v1, (int)D, 0, end_bit, st));
+  ctx->sorted_sel = 1;
+  k_tile_ranges<KeyT><<<(unsigned)((D + 255) / 256), 256, 0, st>>>(D, k1, start, end);
+  GSB_LAUNCH_CHECK();
+  return GSB200_OK;
+}
+
+// Stage 3-5 (needs D on the host for the buffer sizes and cub's num_items).  Sorted ids go to ids_out, or stay
+// in ctx->vals[ctx->sorted_sel] when ids_out == nullptr.
+int bin_and_sort(gsb200_ctx* ctx, uint32_t N, int64_t D, int tiles_h, int tiles_w, int32_t* ids_out, int32_t* start,
+                 int32_t* end, cudaStream_t st) {
   const uint32_t T = (uint32_t)tiles_h * (uint32_t)tiles_w;
   if (T) {
     k_fill_i32<<<(T + 255) / 256, 256, 0, st>>>(start, -1, T);
@@ -116,31 +193,18 @@ int bin_and_sort(gsb200_ctx* ctx, uint32_t N, int64_t D, const float* depth, int
   }
   ctx->D = D;
   if (D == 0 || N == 0) return GSB200_OK;
+  GSB_CHECK(D < (int64_t)2147483647, GSB200_ERR_INVALID, "N_with_dub %lld exceeds int32", (long long)D);
+  const bool k16 = T <= 65536;
+  const size_t kb = k16 ? 2 : 4;
   int rc;
   for (int k = 0; k < 2; ++k) {
-    if ((rc = ctx->keys[k].reserve((size_t)D * 8))) return rc;
+    if ((rc = ctx->keys[k].reserve((size_t)D * kb))) return rc;
     if (!(k == 1 && ids_out)) {
       if ((rc = ctx->vals[k].reserve((size_t)D * 4))) return rc;
     }
   }
-  uint64_t* k0 = ctx->keys[0].as<uint64_t>();
-  uint64_t* k1 = ctx->keys[1].as<uint64_t>();
-  int32_t* v0 = ctx->vals[0].as<int32_t>();
-  int32_t* v1 = ids_out ? ids_out : ctx->vals[1].as<int32_t>();
-  uint32_t warps = (N + 31) / 32;
-  k_emit_keys<<<(warps * 32 + 255) / 256, 256, 0, st>>>(N, ctx->count.as<int32_t>(), ctx->incl.as<int32_t>(),
-                                                       ctx->rect.as<ushort4>(), depth, tiles_w, k0, v0);
-  GSB_LAUNCH_CHECK();
-  GSB_CHECK(D < (int64_t)2147483647, GSB200_ERR_INVALID, "N_with_dub %lld exceeds int32", (long long)D);
-  const int end_bit = 32 + bits_for(T);
-  size_t bytes = 0;
-  GSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0, k1, v0, v1, (int)D, 0, end_bit, st));
-  if ((rc = ctx->cub_tmp.reserve(bytes))) return rc;
-  GSB_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, bytes, k0, k1, v0, v1, (int)D, 0, end_bit, st));
-  ctx->sorted_sel = 1;
-  k_tile_ranges<<<(unsigned)((D + 255) / 256), 256, 0, st>>>(D, k1, start, end);
-  GSB_LAUNCH_CHECK();
-  return GSB200_OK;
+  return k16 ? emit_sort_ranges<uint16_t>(ctx, N, D, tiles_w, T, ids_out, start, end, st)
+             : emit_sort_ranges<uint32_t>(ctx, N, D, tiles_w, T, ids_out, start, end, st);
 }
 
 }  // namespace gsb

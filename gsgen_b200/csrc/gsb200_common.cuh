@@ -64,7 +64,10 @@ struct gsb200_ctx {
   gsb::Buf pay;       // float4[N]           16 B  (r,g,b,depth) or (scalar,-,-,-)
   gsb::Buf rect;      // ushort4[N]           8 B  tile rectangle
   gsb::Buf count;     // int32[N]
-  gsb::Buf incl;      // int32[N]            inclusive scan of count
+  gsb::Buf incl;      // int32[N]            inclusive scan of count (in depth order)
+  gsb::Buf count_sorted;  // int32[N]        count gathered in depth order
+  gsb::Buf dkeys[2];  // uint32[N]           depth bits (radix sort double buffer)
+  gsb::Buf perm[2];   // int32[N]            Gaussian indices in depth order
   gsb::Buf ggeom;     // float[N*8]          gradient record (gmx,gmy,gxx,gxy | gyy,galpha,gdepth,-)
   gsb::Buf gpay;      // float[N*4]          (gr,gg,gb,-)
   // per-duplicate
@@ -75,7 +78,8 @@ struct gsb200_ctx {
   gsb::Buf start, end;  // int32[T]
   // host-visible scalars
   int64_t* h_total = nullptr;  // pinned
-  gsb::Buf d_total;            // int64[1]
+  gsb::Buf d_total;            // unsigned long long[1] device-side duplicate counter
+  cudaEvent_t ev_total = nullptr;
   // saved view state
   uint32_t N = 0;
   int64_t D = 0;

@@ -62,25 +62,28 @@ int launch_project_bwd(uint32_t N, const float* mean, const float* qvec, const f
                        const float* g_m2, const float* g_cov, const float* g_depth, float* g_mean, float* g_qvec,
                        float* g_svec, cudaStream_t st);
 int launch_aabb_count(uint32_t N, const float* mean2d, const float* cov2d, int tile, float fx, float fy, float cx,
-                      float cy, int W, int H, float D, int32_t* tl, int32_t* br, int32_t* count, cudaStream_t st);
+                      float cy, int W, int H, float D, int32_t* tl, int32_t* br, unsigned long long* total,
+                      cudaStream_t st);
 int launch_count_from_aabb(uint32_t N, const int32_t* tl, const int32_t* br, int32_t* count, ushort4* rect,
-                           cudaStream_t st);
+                           unsigned long long* total, cudaStream_t st);
 int launch_pack_splats(uint32_t N, const float* mean2d, const float* cov2d, const float* alpha, const float* payload,
                        int pay_kind, Splat* splat, float4* pay, cudaStream_t st);
 int launch_preprocess(uint32_t N, const float* mean, const float* qvec, const float* svec, const float* alpha,
                       const float* color, const Camera& cam, float* mean2d, float* cov2d, float* depthg,
                       uint8_t* mask, float* radii2d, Splat* splat, float4* pay, ushort4* rect, int32_t* count,
-                      cudaStream_t st);
+                      unsigned long long* total, cudaStream_t st);
 int launch_project_bwd_fused(uint32_t N, const float* mean, const float* qvec, const float* svec,
                              const uint8_t* mask, const Camera& cam, const float4* ggeom, const float4* gpay,
                              float* g_mean, float* g_qvec, float* g_svec, float* g_alpha, float* g_color,
-                             float* g_mean2d, cudaStream_t st);
+                             float* g_mean2d, int accumulate, cudaStream_t st);
 
 // binning.cu
-int scan_counts(gsb200_ctx* ctx, uint32_t N, cudaStream_t st);
-int read_total(gsb200_ctx* ctx, uint32_t N, int64_t* h_total, cudaStream_t st);
-int bin_and_sort(gsb200_ctx* ctx, uint32_t N, int64_t D, const float* depth, int tiles_h, int tiles_w,
-                 int32_t* ids_out, int32_t* start, int32_t* end, cudaStream_t st);
+int begin_total(gsb200_ctx* ctx, cudaStream_t st);    // zero the device-side duplicate counter
+int request_total(gsb200_ctx* ctx, cudaStream_t st);  // async D2H copy + event
+int wait_total(gsb200_ctx* ctx, int64_t* h_total);    // host waits for that event only
+int sort_depths_and_scan(gsb200_ctx* ctx, uint32_t N, const float* depth, cudaStream_t st);
+int bin_and_sort(gsb200_ctx* ctx, uint32_t N, int64_t D, int tiles_h, int tiles_w, int32_t* ids_out, int32_t* start,
+                 int32_t* end, cudaStream_t st);
 
 // composite_fwd.cu / composite_bwd.cu
 int launch_composite_fwd(int pay_kind, int C, bool extras, const CompositeArgs& a, cudaStream_t st);

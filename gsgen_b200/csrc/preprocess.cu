@@ -12,6 +12,21 @@ namespace gsb {
 
 constexpr int kThreads = 256;
 
+// adds the block's sum of per-thread duplicate counts into *total (one 64-bit atomic per block); must be reached
+// by every thread of the block
+__device__ __forceinline__ void block_add_total(int v, unsigned long long* total) {
+  __shared__ int s_part[kThreads / 32];
+  v = __reduce_add_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0 && total) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; ++i) t += s_part[i];
+    if (t) atomicAdd(total, (unsigned long long)t);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_cull_bsphere(uint32_t N, const float* __restrict__ mean, const float* __restrict__ svec,
                const float* __restrict__ normal, const float* __restrict__ pts, uint8_t* __restrict__ mask,
@@ -80,29 +95,36 @@ k_project_bwd(uint32_t N, const float* __restrict__ mean, const float* __restric
 __global__ void __launch_bounds__(kThreads)
 k_aabb_count(uint32_t N, const float* __restrict__ mean2d, const float* __restrict__ cov2d, int tile, float fx,
              float fy, float cx, float cy, int W, int H, float D, int32_t* __restrict__ tl,
-             int32_t* __restrict__ br, int32_t* __restrict__ count) {
+             int32_t* __restrict__ br, unsigned long long* __restrict__ total) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  float2 m = reinterpret_cast<const float2*>(mean2d)[i];
-  float4 c = reinterpret_cast<const float4*>(cov2d)[i];
-  float m2[2] = {m.x, m.y};
-  int r[4];
-  aabb_tiles(m2, c.x, c.w, D, fx, fy, cx, cy, W, H, tile, r);
-  reinterpret_cast<int2*>(tl)[i] = make_int2(r[0], r[1]);
-  reinterpret_cast<int2*>(br)[i] = make_int2(r[2], r[3]);
-  count[i] = (r[2] - r[0] + 1) * (r[3] - r[1] + 1);
+  int cnt = 0;
+  if (i < N) {
+    float2 m = reinterpret_cast<const float2*>(mean2d)[i];
+    float4 c = reinterpret_cast<const float4*>(cov2d)[i];
+    float m2[2] = {m.x, m.y};
+    int r[4];
+    aabb_tiles(m2, c.x, c.w, D, fx, fy, cx, cy, W, H, tile, r);
+    reinterpret_cast<int2*>(tl)[i] = make_int2(r[0], r[1]);
+    reinterpret_cast<int2*>(br)[i] = make_int2(r[2], r[3]);
+    cnt = (r[2] - r[0] + 1) * (r[3] - r[1] + 1);
+  }
+  block_add_total(cnt, total);
 }
 
 // counts from caller-provided AABBs (reference-compatible binning op)
 __global__ void __launch_bounds__(kThreads)
 k_count_from_aabb(uint32_t N, const int32_t* __restrict__ tl, const int32_t* __restrict__ br,
-                  int32_t* __restrict__ count, ushort4* __restrict__ rect) {
+                  int32_t* __restrict__ count, ushort4* __restrict__ rect, unsigned long long* __restrict__ total) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  int2 a = reinterpret_cast<const int2*>(tl)[i], b = reinterpret_cast<const int2*>(br)[i];
-  int w = b.x - a.x + 1, h = b.y - a.y + 1;
-  count[i] = (w > 0 && h > 0) ? w * h : 0;
-  rect[i] = make_ushort4((unsigned short)a.x, (unsigned short)a.y, (unsigned short)b.x, (unsigned short)b.y);
+  int cnt = 0;
+  if (i < N) {
+    int2 a = reinterpret_cast<const int2*>(tl)[i], b = reinterpret_cast<const int2*>(br)[i];
+    int w = b.x - a.x + 1, h = b.y - a.y + 1;
+    cnt = (w > 0 && h > 0) ? w * h : 0;
+    count[i] = cnt;
+    rect[i] = make_ushort4((unsigned short)a.x, (unsigned short)a.y, (unsigned short)b.x, (unsigned short)b.y);
+  }
+  block_add_total(cnt, total);
 }
 
 // payload kinds: 0 none (SH path: payload fetched from the caller's sh tensor), 1 RGB [N,3], 2 scalar [>=N]
@@ -126,14 +148,11 @@ k_pack_splats(uint32_t N, const float* __restrict__ mean2d, const float* __restr
 // ---------------------------------------------------------------------------------------------------
 // fused front end: cull + project + radius + AABB + count + splat record.  84 B/Gaussian algorithmic.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-k_preprocess(uint32_t N, const float* __restrict__ mean, const float* __restrict__ qvec,
-             const float* __restrict__ svec, const float* __restrict__ alpha, const float* __restrict__ color,
-             Camera cam, float* __restrict__ mean2d, float* __restrict__ cov2d, float* __restrict__ depthg,
-             uint8_t* __restrict__ mask, float* __restrict__ radii2d, Splat* __restrict__ splat,
-             float4* __restrict__ pay, ushort4* __restrict__ rect, int32_t* __restrict__ count) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
+__device__ __forceinline__ int preprocess_one(
+    uint32_t i, const float* __restrict__ mean, const float* __restrict__ qvec, const float* __restrict__ svec,
+    const float* __restrict__ alpha, const float* __restrict__ color, const Camera& cam, float* __restrict__ mean2d,
+    float* __restrict__ cov2d, float* __restrict__ depthg, uint8_t* __restrict__ mask, float* __restrict__ radii2d,
+    Splat* __restrict__ splat, float4* __restrict__ pay, ushort4* __restrict__ rect, int32_t* __restrict__ count) {
   float x[3] = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2]};
   float s[3] = {svec[3 * i], svec[3 * i + 1], svec[3 * i + 2]};
   bool keep = true;
@@ -148,7 +167,7 @@ k_preprocess(uint32_t N, const float* __restrict__ mean, const float* __restrict
     depthg[i] = 0.f;
     if (radii2d) radii2d[i] = 0.f;
     count[i] = 0;
-    return;
+    return 0;
   }
   float4 q4 = reinterpret_cast<const float4*>(qvec)[i];
   float q[4] = {q4.x, q4.y, q4.z, q4.w};
@@ -171,7 +190,23 @@ k_preprocess(uint32_t N, const float* __restrict__ mean, const float* __restrict
   spp[0] = make_float4(sp.mx, sp.my, sp.p0, sp.p1);
   spp[1] = make_float4(sp.p2, sp.a, sp.hx, sp.hy);
   if (color) pay[i] = make_float4(color[3 * i], color[3 * i + 1], color[3 * i + 2], f.depth);
+  return cnt;
 }
+
+__global__ void __launch_bounds__(kThreads)
+k_preprocess(uint32_t N, const float* __restrict__ mean, const float* __restrict__ qvec,
+             const float* __restrict__ svec, const float* __restrict__ alpha, const float* __restrict__ color,
+             Camera cam, float* __restrict__ mean2d, float* __restrict__ cov2d, float* __restrict__ depthg,
+             uint8_t* __restrict__ mask, float* __restrict__ radii2d, Splat* __restrict__ splat,
+             float4* __restrict__ pay, ushort4* __restrict__ rect, int32_t* __restrict__ count,
+             unsigned long long* __restrict__ total) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  block_add_total(i < N ? preprocess_one(i, mean, qvec, svec, alpha, color, cam, mean2d, cov2d, depthg, mask, radii2d,
+                                         splat, pay, rect, count)
+                        : 0,
+                  total);
+}
+
 
 // ---------------------------------------------------------------------------------------------------
 // fused back end: gradient records of the composite backward -> parameter gradients (all written).
@@ -182,12 +217,13 @@ k_project_bwd_fused(uint32_t N, const float* __restrict__ mean, const float* __r
                     const float* __restrict__ svec, const uint8_t* __restrict__ mask, Camera cam,
                     const float4* __restrict__ ggeom, const float4* __restrict__ gpay, float* __restrict__ g_mean,
                     float* __restrict__ g_qvec, float* __restrict__ g_svec, float* __restrict__ g_alpha,
-                    float* __restrict__ g_color, float* __restrict__ g_mean2d) {
+                    float* __restrict__ g_color, float* __restrict__ g_mean2d, int accumulate) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   float gx[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f};
   float ga = 0.f, gcol[3] = {0.f, 0.f, 0.f}, gm2[2] = {0.f, 0.f};
-  if (mask[i]) {
+  const bool vis = mask[i] != 0;
+  if (vis) {
     float4 g0 = ggeom[2 * i], g1 = ggeom[2 * i + 1];
     float x[3] = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2]};
     float4 q4 = reinterpret_cast<const float4*>(qvec)[i];
@@ -201,6 +237,20 @@ k_project_bwd_fused(uint32_t N, const float* __restrict__ mean, const float* __r
     ga = g1.y;
     if (gpay) { float4 p = gpay[i]; gcol[0] = p.x; gcol[1] = p.y; gcol[2] = p.z; }
   }
+  if (g_mean2d) reinterpret_cast<float2*>(g_mean2d)[i] = make_float2(gm2[0], gm2[1]);
+  if (accumulate) {  // += into the caller's running gradient (e.g. the flat all-reduce buffer); culled: no traffic
+    if (!vis) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { g_mean[3 * i + k] += gx[k]; g_svec[3 * i + k] += gs[k]; }
+    float4 o = reinterpret_cast<float4*>(g_qvec)[i];
+    reinterpret_cast<float4*>(g_qvec)[i] = make_float4(o.x + gq[0], o.y + gq[1], o.z + gq[2], o.w + gq[3]);
+    g_alpha[i] += ga;
+    if (g_color) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) g_color[3 * i + k] += gcol[k];
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < 3; ++k) { g_mean[3 * i + k] = gx[k]; g_svec[3 * i + k] = gs[k]; }
   reinterpret_cast<float4*>(g_qvec)[i] = make_float4(gq[0], gq[1], gq[2], gq[3]);
@@ -209,7 +259,6 @@ k_project_bwd_fused(uint32_t N, const float* __restrict__ mean, const float* __r
 #pragma unroll
     for (int k = 0; k < 3; ++k) g_color[3 * i + k] = gcol[k];
   }
-  if (g_mean2d) reinterpret_cast<float2*>(g_mean2d)[i] = make_float2(gm2[0], gm2[1]);
 }
 
 // ---- host launchers ----------------------------------------------------------------------------------
@@ -239,16 +288,17 @@ int launch_project_bwd(uint32_t N, const float* mean, const float* qvec, const f
   return GSB200_OK;
 }
 int launch_aabb_count(uint32_t N, const float* mean2d, const float* cov2d, int tile, float fx, float fy, float cx,
-                      float cy, int W, int H, float D, int32_t* tl, int32_t* br, int32_t* count, cudaStream_t st) {
+                      float cy, int W, int H, float D, int32_t* tl, int32_t* br, unsigned long long* total,
+                      cudaStream_t st) {
   if (N == 0) return GSB200_OK;
-  k_aabb_count<<<grid1d(N), kThreads, 0, st>>>(N, mean2d, cov2d, tile, fx, fy, cx, cy, W, H, D, tl, br, count);
+  k_aabb_count<<<grid1d(N), kThreads, 0, st>>>(N, mean2d, cov2d, tile, fx, fy, cx, cy, W, H, D, tl, br, total);
   GSB_LAUNCH_CHECK();
   return GSB200_OK;
 }
 int launch_count_from_aabb(uint32_t N, const int32_t* tl, const int32_t* br, int32_t* count, ushort4* rect,
-                           cudaStream_t st) {
+                           unsigned long long* total, cudaStream_t st) {
   if (N == 0) return GSB200_OK;
-  k_count_from_aabb<<<grid1d(N), kThreads, 0, st>>>(N, tl, br, count, rect);
+  k_count_from_aabb<<<grid1d(N), kThreads, 0, st>>>(N, tl, br, count, rect, total);
   GSB_LAUNCH_CHECK();
   return GSB200_OK;
 }
@@ -262,20 +312,20 @@ int launch_pack_splats(uint32_t N, const float* mean2d, const float* cov2d, cons
 int launch_preprocess(uint32_t N, const float* mean, const float* qvec, const float* svec, const float* alpha,
                       const float* color, const Camera& cam, float* mean2d, float* cov2d, float* depthg,
                       uint8_t* mask, float* radii2d, Splat* splat, float4* pay, ushort4* rect, int32_t* count,
-                      cudaStream_t st) {
+                      unsigned long long* total, cudaStream_t st) {
   if (N == 0) return GSB200_OK;
   k_preprocess<<<grid1d(N), kThreads, 0, st>>>(N, mean, qvec, svec, alpha, color, cam, mean2d, cov2d, depthg, mask,
-                                              radii2d, splat, pay, rect, count);
+                                              radii2d, splat, pay, rect, count, total);
   GSB_LAUNCH_CHECK();
   return GSB200_OK;
 }
 int launch_project_bwd_fused(uint32_t N, const float* mean, const float* qvec, const float* svec,
                              const uint8_t* mask, const Camera& cam, const float4* ggeom, const float4* gpay,
                              float* g_mean, float* g_qvec, float* g_svec, float* g_alpha, float* g_color,
-                             float* g_mean2d, cudaStream_t st) {
+                             float* g_mean2d, int accumulate, cudaStream_t st) {
   if (N == 0) return GSB200_OK;
   k_project_bwd_fused<<<grid1d(N), kThreads, 0, st>>>(N, mean, qvec, svec, mask, cam, ggeom, gpay, g_mean, g_qvec,
-                                                     g_svec, g_alpha, g_color, g_mean2d);
+                                                     g_svec, g_alpha, g_color, g_mean2d, accumulate);
   GSB_LAUNCH_CHECK();
   return GSB200_OK;
 }

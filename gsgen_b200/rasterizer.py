@@ -46,7 +46,7 @@ class _RenderView(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mean, qvec, svec, alpha, color, sh, bg, cam: Gsb200Camera, C, sh_c2w9, bg_rgb, rgb_only, slot,
-                aux):
+                aux, grad_sink):
         dev = mean.device
         N = mean.shape[0]
         H, W = cam.H, cam.W
@@ -95,6 +95,7 @@ class _RenderView(torch.autograd.Function):
                                                     _lib.stream_ptr(dev)))
         ctx.save_for_backward(mean, qvec, svec, alpha, color, sh, bg, bg_rgb, rgb, depth, opacity, z2, T, mask)
         ctx.cam, ctx.C, ctx.sh_c2w9, ctx.slot, ctx.extras, ctx.aux = cam, C, sh_c2w9, slot, extras, aux
+        ctx.grad_sink = grad_sink
         if aux is not None:
             aux.update(mask=mask, cov2d=cov2d, depth=depthg, radii2d=radii, N_with_dub=int(ndup.value))
         ctx.mark_non_differentiable(T)
@@ -128,10 +129,18 @@ class _RenderView(torch.autograd.Function):
             g.g_opacity, g.opacity = fptr(g_opacity), fptr(opacity)
             g.g_z2, g.z2 = fptr(g_z2), fptr(z2)
         g.T, g.mask = fptr(T), ptr(mask, torch.bool)
-        gm, gq, gs = torch.empty_like(mean), torch.empty_like(qvec), torch.empty_like(svec)
-        ga = torch.empty_like(alpha)
-        gcol = torch.empty_like(color) if not is_sh else None
-        gsh = torch.zeros_like(sh) if is_sh else None
+        sink = ctx.grad_sink
+        if sink is not None:  # accumulate straight into the caller's buffers (views of the flat all-reduce operand)
+            gm, gq, gs, ga = sink["mean"], sink["qvec"], sink["svec"], sink["alpha"]
+            gcol = sink["color"] if not is_sh else None
+            gsh = sink["sh"] if is_sh else None
+            g.accumulate = 1
+        else:
+            gm, gq, gs = torch.empty_like(mean), torch.empty_like(qvec), torch.empty_like(svec)
+            ga = torch.empty_like(alpha)
+            gcol = torch.empty_like(color) if not is_sh else None
+            gsh = torch.zeros_like(sh) if is_sh else None
+            g.accumulate = 0
         gm2 = torch.empty(N, 2, device=dev, dtype=torch.float32)
         need_bg = (not is_sh) and bg is not None and ctx.needs_input_grad[6]
         gbg = torch.empty_like(bg) if need_bg else None
@@ -142,14 +151,20 @@ class _RenderView(torch.autograd.Function):
                                                      _lib.stream_ptr(dev)))
         if ctx.aux is not None:  # what mean_2d.grad holds in the reference (retain_grad, :1247)
             ctx.aux["mean2d_grad"] = gm2
-        return gm, gq, gs, ga, gcol, gsh, gbg, None, None, None, None, None, None, None
+        if sink is not None:
+            return None, None, None, None, None, None, gbg, None, None, None, None, None, None, None, None
+        return gm, gq, gs, ga, gcol, gsh, gbg, None, None, None, None, None, None, None, None
 
 
 def render_view(mean, qvec, svec, alpha, c2w, camera_info, *, color=None, sh=None, C: int = 1, bg=None, bg_rgb=None,
                 rgb_only: bool = False, sh_c2w=None, frustum_radius=6.0, tile_radius=6.0, T_thresh=1e-4,
-                skip_frustum_culling=False, depth_detach=True, slot: int = 0):
+                skip_frustum_culling=False, depth_detach=True, slot: int = 0, grad_sink=None):
     """One view through the fused path.  Returns the dict `render_one` returns
     ({"rgb","depth","opacity","z_var"} (+"T")) plus "aux" (mask, mean2d, cov2d, depth, radii2d, N_with_dub).
+
+    grad_sink: optional dict name -> fp32 tensor (mean, qvec, svec, alpha, color | sh) shaped like the parameters;
+                the backward then ADDS the view's gradients into these tensors (e.g. views of one flat buffer that is
+                all-reduced once per step) and autograd receives None for them -- no zero-fill / add pass per view.
 
     color given -> RGB path (render_with_T + 3x render_scalar semantics, per-pixel bg[H,W,3]);
     sh given    -> SH path  (render_sh / render_sh_bg semantics, constant bg_rgb[3]); `sh_c2w` is the tensor the
@@ -166,7 +181,7 @@ def render_view(mean, qvec, svec, alpha, c2w, camera_info, *, color=None, sh=Non
         sh_c2w9 = src.detach().to("cpu", torch.float32).contiguous().view(-1)[:9].tolist()
     aux = {}
     rgb, depth, opacity, z2, T, mean2d = _RenderView.apply(mean, qvec, svec, alpha, color, sh, bg, cam, C, sh_c2w9,
-                                                           bg_rgb, rgb_only or sh is not None, slot, aux)
+                                                           bg_rgb, rgb_only or sh is not None, slot, aux, grad_sink)
     out = {"rgb": rgb, "T": T}
     if sh is None and not rgb_only:
         out.update(depth=depth, opacity=opacity, z_var=z2 - depth * depth)

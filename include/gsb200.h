@@ -210,16 +210,19 @@ typedef struct gsb200_view_grads {
   const float* g_z2;      const float* z2;
   const float* T;                                 /* [H,W] (for g_bg)                               */
   const uint8_t* mask;                            /* [N] frustum mask written by the forward        */
-  /* outputs, all WRITTEN (culled Gaussians get zeros) */
+  /* outputs: WRITTEN (culled Gaussians get zeros), or -- when `accumulate` != 0 -- ADDED to what the buffers
+   * hold, so that a multi-view step sums straight into one flat gradient buffer (the NCCL all-reduce operand)
+   * without a zero-fill + add pass per view */
   float* g_mean;    /* [N,3]                                                                       */
   float* g_qvec;    /* [N,4]                                                                       */
   float* g_svec;    /* [N,3]                                                                       */
   float* g_alpha;   /* [N]                                                                         */
   float* g_color;   /* [N,3] (RGB path) or NULL                                                    */
-  float* g_sh;      /* [N,3,C*C] (SH path) or NULL; must be zero-filled by the caller              */
+  float* g_sh;      /* [N,3,C*C] (SH path) or NULL; always accumulated into (zero-fill it first)   */
   float* g_mean2d;  /* [N,2] or NULL: gradient w.r.t. the projected mean (densification statistic,  */
                     /*                gaussian_splatting.py:464-469)                                */
   float* g_bg;      /* [H,W,3] or NULL: nan_to_num(g_rgb * T) (gs/renderer.py:1282)                 */
+  int32_t accumulate;
 } gsb200_view_grads;
 
 int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* cam, const gsb200_view_in* in,

@@ -177,3 +177,27 @@ def test_forward_is_deterministic_and_backward_stable():
         grads.append(sh.grad.clone())
     assert torch.equal(outs[0], outs[1])  # forward: bit-identical
     assert_grad_close(grads[0], grads[1], 1e-5, "run-to-run g_sh")  # float atomics: order noise only
+
+
+def test_grad_sink_accumulates():
+    """backward(grad_sink=...) ADDS into the caller's buffers (the flat all-reduce operand): two views == sum."""
+    from gsgen_b200.rasterizer import render_view
+
+    sc = make_scene("c3", N=5000, reso=128).to(DEV)
+    sc.svec = (sc.svec * 3.0).contiguous()
+    cam, c2w = sc.cams[0], sc.c2ws[0].cpu()
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(cam.h, cam.w, 3, generator=g).to(DEV)
+    leaves = lambda: [t.clone().requires_grad_() for t in (sc.mean, sc.qvec, sc.svec, sc.alpha, sc.sh)]
+    m, q, s, a, sh = leaves()
+    out = render_view(m, q, s, a, c2w, cam, sh=sh, C=4)
+    out["rgb"].backward(gradient=w)
+    ref = dict(mean=m.grad, qvec=q.grad, svec=s.grad, alpha=a.grad, sh=sh.grad)
+    sink = {k: torch.zeros_like(v) for k, v in ref.items()}
+    for _ in range(2):
+        m2, q2, s2, a2, sh2 = leaves()
+        out = render_view(m2, q2, s2, a2, c2w, cam, sh=sh2, C=4, grad_sink=sink)
+        out["rgb"].backward(gradient=w)
+        assert m2.grad is None and sh2.grad is None
+    for k in ref:
+        assert_grad_close(sink[k], 2 * ref[k], 1e-5, f"sink {k}")
