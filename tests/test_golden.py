@@ -46,8 +46,8 @@ def test_oracle_reproduces_reference_golden(oracle_mod, name):
     m2, c2, col, al, tlf = z["in_mean2d"], z["in_cov2d"], z["in_color"], z["in_alpha"], z["in_topleft"]
     # K5
     out, T, stats, margin = o.composite_rgb_fwd(m2, c2, col, al, start, end, ids, tlf, cfg, want_margin=True)
-    assert_image_close(out, z["ref_rgb"], margin, what="K5 rgb", atol=2e-6)
-    assert_image_close(T, z["ref_T"].view(H, W), margin, what="K5 T", atol=2e-6)
+    assert_image_close(out, z["ref_rgb"], margin, what="K5 rgb", atol=1e-5)
+    assert_image_close(T, z["ref_T"].view(H, W), margin, what="K5 T", atol=1e-5)
     # K6
     final = z["ref_rgb"] + z["ref_T"] * z["in_bg"]
     gm, gc, gcol, ga = o.composite_rgb_bwd(m2, c2, col, al, start, end, ids, final, z["in_gout"], tlf, cfg)
@@ -58,7 +58,7 @@ def test_oracle_reproduces_reference_golden(oracle_mod, name):
     # K7 / K8
     so, sT = o.composite_scalar_fwd(m2, c2, z["in_depth"].view(-1), al, start, end, ids, tlf, cfg)
     zs = max(1.0, float(z["ref_scalar"].abs().max()))
-    assert_image_close(so / zs, z["ref_scalar"].view(H, W) / zs, margin, what="K7", atol=2e-6)
+    assert_image_close(so / zs, z["ref_scalar"].view(H, W) / zs, margin, what="K7", atol=1e-5)
     gm, gc, gs, ga = o.composite_scalar_bwd(m2, c2, z["in_depth"].view(-1), al, start, end, ids,
                                             z["ref_scalar"].view(H, W), z["in_g_scalar_out"].view(H, W), tlf, cfg)
     assert_grad_close(gm, z["ref_s_g_mean2d"], 2e-4, "K8 g_mean2d")
@@ -72,7 +72,7 @@ def test_oracle_reproduces_reference_golden(oracle_mod, name):
         sh = z[f"in_sh{C}"]
         out, T, stats, mg = o.composite_sh_fwd(m2, c2, sh, al, start, end, ids, tlf, z["in_c2w"], C, cfg,
                                                z["in_bg_rgb"] if with_bg else None, want_margin=True)
-        assert_image_close(out, z[f"ref_{tag}_rgb"].view(H, W, 3), mg, what=f"{tag} rgb", atol=5e-6)
+        assert_image_close(out, z[f"ref_{tag}_rgb"].view(H, W, 3), mg, what=f"{tag} rgb", atol=1e-5)
         gm, gc, gsh, ga = o.composite_sh_bwd(m2, c2, sh, al, start, end, ids, z[f"ref_{tag}_rgb"].view(H, W, 3),
                                              z["in_gout_sh"].view(H, W, 3), tlf, z["in_c2w"], C, cfg)
         assert_grad_close(gm, z[f"ref_{tag}_g_mean2d"], 3e-4, f"{tag} g_mean2d")
