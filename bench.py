@@ -39,7 +39,7 @@ SH_C = {"c1": 1, "c2": 3, "c3": 4, "c4": 4, "c5": 4}
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(SH_C))
@@ -81,7 +81,8 @@ def algorithmic_bytes(C, D, D_eff, N, N0, T, H, W):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons, sampled every 50 ms.  Started BEFORE the warm-up (NVML start-up can
+    stall CUDA calls for hundreds of ms) and marked at the start / end of the timed region."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -95,25 +96,34 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def mark(self):
+        self.f.flush()
+        try:
+            return os.path.getsize(self.f.name)
+        except OSError:
+            return 0
+
+    def stop(self, begin=0, end=None):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
         self.f.flush()
-        self.f.seek(0)
+        data = open(self.f.name).read()
+        # samples taken inside [begin, end) of the log = during the timed region (one line either side kept)
+        lo = max(0, data.rfind("\n", 0, begin) + 1) if begin else 0
+        hi = len(data) if end is None else (data.find("\n", end) + 1 or len(data))
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().strip().splitlines():
+        for line in data[lo:hi].strip().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
@@ -334,7 +344,12 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
-    # ---- warm-up
+    # ---- warm-up (clock sampler already running)
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    if rank == 0:
+        sampler.start()
+        time.sleep(1.0)
     for _ in range(max(3, args.warmup)):
         step()
     torch.cuda.synchronize()
@@ -349,19 +364,17 @@ def run_ours(args):
         _lib.check(_lib.lib().gsb200_ctx_get_profile(c, hm, hc, 1))
 
     # ---- timed region: exactly K steps, barrier + synchronize on both sides, CUDA events on the stream
-    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(); torch.cuda.synchronize()
+    mark0 = sampler.mark() if rank == 0 else 0
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize(); barrier()
     ms = e0.elapsed_time(e1) / args.steps
-    clocks = sampler.stop() if rank == 0 else None
+    mark1 = sampler.mark() if rank == 0 else 0
+    clocks = None  # filled after the e2e loop (the sampler keeps running; only the timed region's lines are used)
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -443,6 +456,8 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    time.sleep(0.1)
+    clocks = sampler.stop(mark0, mark1)
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
         try:

@@ -12,7 +12,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgsb200.so")
+LIB_PATH = os.environ.get("GSB200_LIB", os.path.join(_HERE, "libgsb200.so"))  # env override: tuning builds only
 
 c_void = ctypes.c_void_p
 c_u32 = ctypes.c_uint32

@@ -31,14 +31,16 @@ def _deps_mtime() -> float:
     return m
 
 
-def build(force: bool = False, ptxas_v: bool = False, verbose: bool = True) -> str:
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
-        return LIB
+def build(force: bool = False, ptxas_v: bool = False, verbose: bool = True, defines=(), out: str = LIB) -> str:
+    """defines: extra -D flags (tuning experiments); out: output .so (default: the in-tree library)."""
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= _deps_mtime():
+        return out
     os.makedirs(BUILD, exist_ok=True)
-    flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if ptxas_v else [])
+    flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if ptxas_v else []) + [f"-D{d}" for d in defines]
+    tag = ("_" + "_".join(d.replace("=", "") for d in defines)) if defines else ""
 
     def compile_one(src):
-        obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+        obj = os.path.join(BUILD, src.replace(".cu", tag + ".o"))
         cmd = ["nvcc", *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r
@@ -51,10 +53,12 @@ def build(force: bool = False, ptxas_v: bool = False, verbose: bool = True) -> s
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed on {src}")
             objs.append(obj)
-    cmd = ["nvcc", "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = ["nvcc", "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, ptxas_v="--ptxas-v" in sys.argv))
+    _defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    _out = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")), LIB)
+    print(build(force="--force" in sys.argv or bool(_defs), ptxas_v="--ptxas-v" in sys.argv, defines=_defs, out=_out))

@@ -67,16 +67,19 @@ k_emit_tiles(uint32_t N, const int32_t* __restrict__ perm, const int32_t* __rest
   while (have) {
     int g = __ffs(have) - 1;
     have &= have - 1;
-    int cg = __shfl_sync(0xffffffffu, c, g);
     int og = __shfl_sync(0xffffffffu, off, g);
     int idg = __shfl_sync(0xffffffffu, gid, g);
     int x0 = __shfl_sync(0xffffffffu, (int)r.x, g), y0 = __shfl_sync(0xffffffffu, (int)r.y, g);
-    int x1 = __shfl_sync(0xffffffffu, (int)r.z, g);
-    int w = x1 - x0 + 1;
-    for (int k = lane; k < cg; k += 32) {
-      int ty = y0 + k / w, tx = x0 + k % w;
-      keys[og + k] = (KeyT)(ty * tiles_w + tx);
-      vals[og + k] = idg;
+    int x1 = __shfl_sync(0xffffffffu, (int)r.z, g), y1 = __shfl_sync(0xffffffffu, (int)r.w, g);
+    const int w = x1 - x0 + 1;
+    // row by row: no integer division, slots of a row are consecutive
+    for (int ty = y0; ty <= y1; ++ty) {
+      const int row_slot = og + (ty - y0) * w;
+      const int row_tile = ty * tiles_w + x0;
+      for (int x = lane; x < w; x += 32) {
+        keys[row_slot + x] = (KeyT)(row_tile + x);
+        vals[row_slot + x] = idg;
+      }
     }
   }
 }

@@ -14,11 +14,16 @@
 //   g_alpha += pAG*G ; gG = pAG*a*G ; v = S^-1 d ; g_mean2d += gG*v ; g_cov2d += 0.5*gG*v v^T
 //   g_pay_ch += w*go_ch ;  g_sh[c,k] += w*y_c(1-y_c)*go_c*Y_k
 //
-// Where the reference issues 10..55 shared-memory float atomics per (pixel, Gaussian) -- all 256 pixels
-// hitting the same address -- each warp here first reduces its 32 pixels with a halving butterfly
-// (K + K/2 + ... shuffles for K values instead of 5K), then ONE lane per value adds into the per-batch
-// shared accumulator, and each (Gaussian, tile) instance is flushed to HBM once per batch with vector
-// reductions (red.global.add.v4.f32).
+// Reduction over the pixels of a tile.  The reference issues 10..55 shared-memory float atomics per (pixel,
+// Gaussian), all 256 pixels hitting the same address.  Here a warp (32 pixels) reduces first, in one of two ways:
+//   * RGB / scalar / SH degree 0 (<= 16 values): a halving butterfly (K + K/2 + ... shuffles for K values);
+//   * SH degree >= 1 (3*C^2 + 6 values): measured in round 1, the butterfly was 3/4 of this kernel's instructions
+//     (profiles/r1_ncu_full_c3_run2.json).  g_sh[c,k] = sum_p t_c(p) * Y_k(p) is a tiny matrix product, so each
+//     lane stores only its 3 scalars t_c (+6 geometry values) per hit into a per-warp transpose buffer and every 4
+//     hits the warp multiplies [12 x 32] by the block's [32 x C^2] basis with the basis column held in registers
+//     (32 FFMA + 8 broadcast LDS.128 per output row) -- ~80 instructions per hit instead of ~370.
+// One lane per value then adds into the per-batch shared accumulator and each (Gaussian, tile) instance is flushed
+// to HBM once per batch with vector reductions (red.global.add.v4.f32).
 #include "composite_common.cuh"
 
 namespace gsb {
@@ -29,10 +34,20 @@ template <int PAY, int C, bool EXTRAS> struct BwdTraits {
   static constexpr int kVals = 6 + kPayVals;  // gmx gmy gxx gxy gyy galpha | payload grads
   static constexpr int kK = kVals <= 8 ? 8 : (kVals <= 16 ? 16 : (kVals <= 32 ? 32 : 64));
   static constexpr int kStride = (kVals + 3) / 4 * 4;  // floats per accumulator row (16 B aligned rows)
+  // transpose-buffer reduction (SH with C >= 2)
+  static constexpr bool kTbuf = (PAY == PAY_SH) && (CC >= 4);
+  static constexpr int kG = 4;                                   // hits per flush
+  static constexpr int kKL = CC <= 4 ? 4 : 16;                   // lanes along k (power of two >= CC)
+  static constexpr int kJ = 32 / kKL;                            // row groups
+  static constexpr int kTbufFloats = kTbuf ? kG * 9 * 32 : 0;    // per warp
 };
 
+#ifndef GSB_BWD_MINBLOCKS
+#define GSB_BWD_MINBLOCKS 2  // 2 CTAs/SM (<=128 registers); measured against 1 (162 registers, no spills) in round 1
+#endif
+
 template <int PAY, int C, bool EXTRAS, bool FUSED, int B>
-__global__ void __launch_bounds__(kCtaThreads)
+__global__ void __launch_bounds__(kCtaThreads, GSB_BWD_MINBLOCKS)
 k_composite_bwd(const CompositeArgs a) {
   using L = StageLayout<PAY, C, B, true>;
   using PT = PayTraits<PAY, C>;
@@ -41,11 +56,13 @@ k_composite_bwd(const CompositeArgs a) {
   constexpr int K = BT::kK;
   constexpr int NV = BT::kVals;
   constexpr int STR = BT::kStride;
+  constexpr bool TBUF = BT::kTbuf;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t s_bar[2];
   __shared__ unsigned s_touched[B / 32];
 
   float* s_acc = reinterpret_cast<float*>(smem + 2 * L::kBytes);  // [B][STR]
+  float* s_tbuf = s_acc + B * STR;                                // [8 warps][G][9][32] (TBUF only)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y;
@@ -104,8 +121,59 @@ k_composite_bwd(const CompositeArgs a) {
     pixel_dir(pg.px, pg.py, c9, d);
     sh_basis<C>(d[0], d[1], d[2], Y);
   }
-  bool red_writer;
-  const int red_e = red_index<K>(lane, &red_writer);
+  // ---- TBUF: this lane's column of the block's basis matrix, Ycol[p] = Y_k(pixel p), k = lane % KL
+  float* my_t = s_tbuf + warp * BT::kTbufFloats;
+  float Ycol[TBUF ? 32 : 1];
+  const int tk = lane & (BT::kKL - 1);   // k index served by this lane in the flush
+  const int tj = lane / BT::kKL;         // row group
+  if constexpr (TBUF) {
+#pragma unroll
+    for (int k = 0; k < BT::kKL; ++k) my_t[lane * BT::kKL + k] = (k < CC) ? Y[k < CC ? k : 0] : 0.f;
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < 32; ++p) Ycol[p] = my_t[p * BT::kKL + tk];
+    __syncwarp();
+  }
+  int nslot = 0;            // hits buffered in my_t (warp-uniform)
+  unsigned slots = 0u;      // their batch entry indices, 8 bits each
+
+  bool red_writer = false;
+  const int red_e = TBUF ? 0 : red_index<K>(lane, &red_writer);
+
+  // flush of the transpose buffer: rows [h][0..2] x basis -> SH gradients, rows [h][3..8] row sums -> geometry
+  auto flush_tbuf = [&]() {
+    if constexpr (TBUF) {
+      __syncwarp();
+      for (int row = tj; row < nslot * 3; row += BT::kJ) {
+        const int h = row / 3, c = row - 3 * h;
+        const float4* tp = reinterpret_cast<const float4*>(my_t + (h * 9 + c) * 32);
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t = tp[q];
+          acc = fmaf(t.x, Ycol[4 * q], acc); acc = fmaf(t.y, Ycol[4 * q + 1], acc);
+          acc = fmaf(t.z, Ycol[4 * q + 2], acc); acc = fmaf(t.w, Ycol[4 * q + 3], acc);
+        }
+        const int jj = (slots >> (8 * h)) & 255u;
+        if (tk < CC) atomicAdd(s_acc + jj * STR + 6 + c * CC + tk, acc);
+      }
+      for (int r0 = 0; r0 < nslot * 6; r0 += 32) {
+        const int r = r0 + lane;
+        if (r < nslot * 6) {
+          const int h = r / 6, v = r - 6 * h;
+          const float* base = my_t + (h * 9 + 3 + v) * 32;
+          float s = 0.f;
+#pragma unroll
+          for (int p = 0; p < 32; ++p) s += base[(p + lane) & 31];
+          const int jj = (slots >> (8 * h)) & 255u;
+          atomicAdd(s_acc + jj * STR + v, s);
+        }
+      }
+      __syncwarp();
+      nslot = 0;
+      slots = 0u;
+    }
+  };
 
   const int nb = (n + B - 1) / B;
   const int32_t* ids = a.ids + s0;
@@ -159,11 +227,14 @@ k_composite_bwd(const CompositeArgs a) {
           if (!__any_sync(kFull, ok)) continue;
           touched |= 1u << bit;
 
-          float vals[K];
+          float vals[TBUF ? 1 : K];
+          if constexpr (!TBUF) {
 #pragma unroll
-          for (int k = 0; k < K; ++k) vals[k] = 0.f;
+            for (int k = 0; k < K; ++k) vals[k] = 0.f;
+          }
           const float w = ok ? aG * T : 0.f;
           float gc;  // sum_ch go_ch * pay_ch
+          float t0 = 0.f, t1 = 0.f, t2 = 0.f;
           if constexpr (PAY == PAY_SH) {
             const float* shp = reinterpret_cast<const float*>(st + L::kPay) + jj * (3 * CC);
             float y[3];
@@ -185,14 +256,16 @@ k_composite_bwd(const CompositeArgs a) {
               y[c] = sigmoid_fast(s);
             }
             gc = go0 * y[0] + go1 * y[1] + go2 * y[2];
-            const float t0 = w * (y[0] * (1.0f - y[0])) * go0;  // vol_render_sh.h:328-333
-            const float t1 = w * (y[1] * (1.0f - y[1])) * go1;
-            const float t2 = w * (y[2] * (1.0f - y[2])) * go2;
+            t0 = w * (y[0] * (1.0f - y[0])) * go0;  // vol_render_sh.h:328-333
+            t1 = w * (y[1] * (1.0f - y[1])) * go1;
+            t2 = w * (y[2] * (1.0f - y[2])) * go2;
+            if constexpr (!TBUF) {
 #pragma unroll
-            for (int k = 0; k < CC; ++k) {
-              vals[6 + k] = t0 * Y[k];
-              vals[6 + CC + k] = t1 * Y[k];
-              vals[6 + 2 * CC + k] = t2 * Y[k];
+              for (int k = 0; k < CC; ++k) {
+                vals[6 + k] = t0 * Y[k];
+                vals[6 + CC + k] = t1 * Y[k];
+                vals[6 + 2 * CC + k] = t2 * Y[k];
+              }
             }
           } else {
             const float4 p = reinterpret_cast<const float4*>(st + L::kPay)[jj];
@@ -219,28 +292,34 @@ k_composite_bwd(const CompositeArgs a) {
           const float vx = kInvCholScale2 * g0.z * u;                        // (S^-1 d).x
           const float vy = kInvCholScale2 * fmaf(g0.w, u, g1.x * v);         // (S^-1 d).y
           const float hg = 0.5f * gG;
-          vals[0] = gG * vx;
-          vals[1] = gG * vy;
-          vals[2] = hg * vx * vx;
-          vals[3] = hg * vx * vy;
-          vals[4] = hg * vy * vy;
-          vals[5] = pAG * G;  // g_alpha (no clamp gate, vol_render.h:409)
+          const float e0 = gG * vx, e1 = gG * vy, e2 = hg * vx * vx, e3 = hg * vx * vy, e4 = hg * vy * vy;
+          const float e5 = pAG * G;  // g_alpha (no clamp gate, vol_render.h:409)
           if (ok) {
             T = fmaf(-aG, T, T);
             done = T < a.thresh;
           }
-          warp_reduce_halving<K>(vals, lane);
-          float* row = s_acc + jj * STR;
-          if constexpr (K == 64) {
-            if (red_e < NV) atomicAdd(row + red_e, vals[0]);
-            if (red_e + 1 < NV) atomicAdd(row + red_e + 1, vals[1]);
+          if constexpr (TBUF) {
+            float* row = my_t + nslot * (9 * 32) + lane;
+            row[0] = t0; row[32] = t1; row[64] = t2;
+            row[96] = e0; row[128] = e1; row[160] = e2; row[192] = e3; row[224] = e4; row[256] = e5;
+            slots |= (unsigned)jj << (8 * nslot);
+            if (++nslot == BT::kG) flush_tbuf();
           } else {
-            if (red_writer && red_e < NV) atomicAdd(row + red_e, vals[0]);
+            vals[0] = e0; vals[1] = e1; vals[2] = e2; vals[3] = e3; vals[4] = e4; vals[5] = e5;
+            warp_reduce_halving<K>(vals, lane);
+            float* row = s_acc + jj * STR;
+            if constexpr (K == 64) {
+              if (red_e < NV) atomicAdd(row + red_e, vals[0]);
+              if (red_e + 1 < NV) atomicAdd(row + red_e + 1, vals[1]);
+            } else {
+              if (red_writer && red_e < NV) atomicAdd(row + red_e, vals[0]);
+            }
           }
         }
         if (touched && lane == 0) atomicOr(&s_touched[r], touched);
         if (__all_sync(kFull, done)) { warp_done = true; break; }
       }
+      if (nslot) flush_tbuf();  // the batch's staging buffer (and its entry indices) is about to be recycled
     }
     __syncthreads();
     // flush this batch's accumulators: one (Gaussian, tile) instance per thread
@@ -267,7 +346,6 @@ k_composite_bwd(const CompositeArgs a) {
       if constexpr (PAY == PAY_SH) {
         float* dst = a.grad_pay + (size_t)id * (3 * CC);
         if ((3 * CC) % 4 == 0 && ((reinterpret_cast<uintptr_t>(a.grad_pay) & 15) == 0)) {
-          // rows start at g[6]: not 16 B aligned in registers, but the destination is
 #pragma unroll
           for (int k = 0; k < 3 * CC; k += 4) red_add_v4(dst + k, g[6 + k], g[7 + k], g[8 + k], g[9 + k]);
         } else {
@@ -312,7 +390,7 @@ template <int PAY, int C, bool EXTRAS, bool FUSED, int B>
 static int launch_one(const CompositeArgs& a, cudaStream_t st) {
   using L = StageLayout<PAY, C, B, true>;
   using BT = BwdTraits<PAY, C, EXTRAS>;
-  const size_t smem = 2 * (size_t)L::kBytes + (size_t)B * BT::kStride * 4;
+  const size_t smem = 2 * (size_t)L::kBytes + (size_t)B * BT::kStride * 4 + (size_t)8 * BT::kTbufFloats * 4;
   auto kern = k_composite_bwd<PAY, C, EXTRAS, FUSED, B>;
   static bool attr_set[64] = {false};
   if (!attr_set[a.device & 63]) {
@@ -338,8 +416,8 @@ int launch_composite_bwd(int pay_kind, int C, bool extras, bool fused, const Com
       switch (C) {
         case 1: return fused ? launch_one<PAY_SH, 1, false, true, 256>(a, st) : launch_one<PAY_SH, 1, false, false, 256>(a, st);
         case 2: return fused ? launch_one<PAY_SH, 2, false, true, 128>(a, st) : launch_one<PAY_SH, 2, false, false, 128>(a, st);
-        case 3: return fused ? launch_one<PAY_SH, 3, false, true, 128>(a, st) : launch_one<PAY_SH, 3, false, false, 128>(a, st);
-        case 4: return fused ? launch_one<PAY_SH, 4, false, true, 128>(a, st) : launch_one<PAY_SH, 4, false, false, 128>(a, st);
+        case 3: return fused ? launch_one<PAY_SH, 3, false, true, 64>(a, st) : launch_one<PAY_SH, 3, false, false, 64>(a, st);
+        case 4: return fused ? launch_one<PAY_SH, 4, false, true, 64>(a, st) : launch_one<PAY_SH, 4, false, false, 64>(a, st);
         default: break;
       }
     default: break;

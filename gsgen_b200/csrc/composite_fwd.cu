@@ -242,8 +242,8 @@ int launch_composite_fwd(int pay_kind, int C, bool extras, const CompositeArgs& 
       switch (C) {
         case 1: return launch_one<PAY_SH, 1, false, 256>(a, st);
         case 2: return launch_one<PAY_SH, 2, false, 256>(a, st);
-        case 3: return launch_one<PAY_SH, 3, false, 128>(a, st);
-        case 4: return launch_one<PAY_SH, 4, false, 128>(a, st);
+        case 3: return launch_one<PAY_SH, 3, false, 64>(a, st);
+        case 4: return launch_one<PAY_SH, 4, false, 64>(a, st);
         default: break;
       }
     default: break;

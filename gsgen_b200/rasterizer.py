@@ -99,7 +99,8 @@ class _RenderView(torch.autograd.Function):
         if aux is not None:
             aux.update(mask=mask, cov2d=cov2d, depth=depthg, radii2d=radii, N_with_dub=int(ndup.value))
         ctx.mark_non_differentiable(T)
-        zero = rgb.new_zeros(())
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None instead of freshly zero-filled tensors
+        zero = None
         return (rgb, depth if extras else zero, opacity if extras else zero, z2 if extras else zero, T, mean2d)
 
     @staticmethod

@@ -33,7 +33,7 @@ def prep(sc, cam, c2w):
     return ocam, normals, pts, cfg
 
 
-def run_case(name, sc, cam, c2w, seed, out_dir, sh_Cs=(1, 2, 3, 4)):
+def run_case(name, sc, cam, c2w, seed, out_dir, sh_variants=((1, False), (4, False), (3, True))):
     import _gs  # the reference extension
 
     dev = torch.device("cuda")
@@ -103,12 +103,12 @@ def run_case(name, sc, cam, c2w, seed, out_dir, sh_Cs=(1, 2, 3, 4)):
     bg_rgb = torch.tensor([0.2, 0.5, 0.7])
     gout_sh = torch.randn(H * W * 3, generator=g)
     res.update(in_bg_rgb=bg_rgb, in_gout_sh=gout_sh)
-    for C in sh_Cs:
+    for C, with_bg in sh_variants:
         gsh = torch.Generator().manual_seed(seed + 10 + C)
         sh = (0.5 * torch.randn(m2.shape[0], 3, C * C, generator=gsh)).contiguous()
         res[f"in_sh{C}"] = sh
         shd = d(sh)
-        for with_bg in (False, True):
+        if True:
             o = torch.zeros(H * W * 3, device=dev)
             gm, gc = torch.zeros_like(m2), torch.zeros_like(c2)
             gshc, ga = torch.zeros_like(shd), torch.zeros_like(al)
@@ -147,12 +147,12 @@ def main():
     sc = make_scene("c3", N=4000, reso=128)
     sc.svec = (sc.svec * 4.0).contiguous()
     cam = CameraInfo(1.1 * 120, 1.1 * 120, 60.0, 50.0, 120, 100, 0.01, 100.0)
-    run_case("g2_dense_4000_120x100", sc, cam, sc.c2ws[0], 202, out_dir, sh_Cs=(2, 4))
-    # G3: the reference's own 2-Gaussian MockRenderer scene (gs/debug.py:52-65), camera scaled by 1/4
+    run_case("g2_dense_4000_120x100", sc, cam, sc.c2ws[0], 202, out_dir, sh_variants=((2, True), (4, False)))
+    # G3: the reference's own 2-Gaussian MockRenderer scene (gs/debug.py:52-65), camera scaled by 1/8
     sc = mock_two_gaussians()
     c0 = sc.cams[0]
-    cam = CameraInfo(c0.fx / 4, c0.fy / 4, c0.cx / 4, c0.cy / 4, c0.w // 4, c0.h // 4, 0.01, 100.0)
-    run_case("g3_mock2_324x210", sc, cam, sc.c2ws[0], 303, out_dir, sh_Cs=(2,))
+    cam = CameraInfo(c0.fx / 8, c0.fy / 8, c0.cx / 8, c0.cy / 8, c0.w // 8, c0.h // 8, 0.01, 100.0)
+    run_case("g3_mock2_162x105", sc, cam, sc.c2ws[0], 303, out_dir, sh_variants=((2, False), (2, True)))
 
 
 if __name__ == "__main__":
