@@ -39,8 +39,74 @@ template <int PAY, int C, bool EXTRAS> struct BwdTraits {
   static constexpr int kG = 4;                                   // hits per flush
   static constexpr int kKL = CC <= 4 ? 4 : 16;                   // lanes along k (power of two >= CC)
   static constexpr int kJ = 32 / kKL;                            // row groups
-  static constexpr int kTbufFloats = kTbuf ? kG * 9 * 32 : 0;    // per warp
+  static constexpr int kYsmFloats = kTbuf ? kKL * 36 : 0;        // per warp: basis matrix [k][36] (k-major, padded)
+  static constexpr int kTbufFloats = kTbuf ? kG * 9 * 32 + kYsmFloats : 0;  // per warp
+  static constexpr int kNR = (3 * kG + kJ - 1) / kJ;             // SH rows per lane group in a flush
+  // accumulator row layout: butterfly path [6 geometry | payload]; transpose-buffer path [3*CC sh | 6 geometry]
+  // (keeps the SH part 16 B aligned so the batch flush streams it float4 by float4)
+  static constexpr int kGeoOff = kTbuf ? kPayVals : 0;
+  static constexpr int kPayOff = kTbuf ? 0 : 6;
 };
+
+#ifndef GSB_BWD_FLUSH_INLINE
+#define GSB_BWD_FLUSH_INLINE 0  // 0: the flush is a real call (keeps its 20+ registers out of the hit loop's budget)
+#endif
+#if GSB_BWD_FLUSH_INLINE
+#define GSB_FLUSH_ATTR __device__ __forceinline__
+#else
+#define GSB_FLUSH_ATTR __device__ __noinline__
+#endif
+
+// Flush of a warp's transpose buffer: SH rows [hit*3+c][32 px] x basis Ysm[k][px] -> g_sh partial sums; geometry rows
+// -> plain row sums; both added into the per-batch shared accumulator rows of the hits' list entries (`slots`).
+template <int PAY, int C, bool EXTRAS>
+GSB_FLUSH_ATTR void flush_tbuf_fn(const float* my_t, const float* my_y, float* s_acc, int nslot, unsigned slots,
+                                  int lane) {
+  using BT = BwdTraits<PAY, C, EXTRAS>;
+  constexpr int CC = C * C;
+  constexpr int STR = BT::kStride;
+  const int tk = lane & (BT::kKL - 1);
+  const int tj = lane / BT::kKL;
+  __syncwarp();
+  float acc[BT::kNR];
+#pragma unroll
+  for (int i = 0; i < BT::kNR; ++i) acc[i] = 0.f;
+  const float* trow = my_t + tj * 32;
+  const float* yrow = my_y + tk * 36;
+#pragma unroll 2
+  for (int q = 0; q < 8; ++q) {
+    const float4 y4 = *reinterpret_cast<const float4*>(yrow + 4 * q);
+#pragma unroll
+    for (int i = 0; i < BT::kNR; ++i) {
+      const float4 t = *reinterpret_cast<const float4*>(trow + i * (BT::kJ * 32) + 4 * q);
+      acc[i] = fmaf(t.x, y4.x, acc[i]); acc[i] = fmaf(t.y, y4.y, acc[i]);
+      acc[i] = fmaf(t.z, y4.z, acc[i]); acc[i] = fmaf(t.w, y4.w, acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < BT::kNR; ++i) {
+    const int row = tj + i * BT::kJ;
+    if (row < nslot * 3 && tk < CC) {
+      const int h = row / 3, c = row - 3 * h;
+      const int jj = (slots >> (8 * h)) & 255u;
+      atomicAdd(s_acc + jj * STR + BT::kPayOff + c * CC + tk, acc[i]);
+    }
+  }
+  // geometry: plain row sums, one row per lane (rotated 16-byte reads: conflict-free)
+  if (lane < nslot * 6) {
+    const float* base = my_t + (BT::kG * 3 + lane) * 32;
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(base + 4 * ((q + lane) & 7));
+      s += (t.x + t.y) + (t.z + t.w);
+    }
+    const int h = lane / 6, v = lane - 6 * h;
+    const int jj = (slots >> (8 * h)) & 255u;
+    atomicAdd(s_acc + jj * STR + BT::kGeoOff + v, s);
+  }
+  __syncwarp();
+}
 
 #ifndef GSB_BWD_MINBLOCKS
 #define GSB_BWD_MINBLOCKS 2  // 2 CTAs/SM (<=128 registers); measured against 1 (162 registers, no spills) in round 1
@@ -59,7 +125,7 @@ k_composite_bwd(const CompositeArgs a) {
   constexpr bool TBUF = BT::kTbuf;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t s_bar[2];
-  __shared__ unsigned s_touched[B / 32];
+  __shared__ unsigned s_touched[2][B / 32];
 
   float* s_acc = reinterpret_cast<float*>(smem + 2 * L::kBytes);  // [B][STR]
   float* s_tbuf = s_acc + B * STR;                                // [8 warps][G][9][32] (TBUF only)
@@ -90,7 +156,7 @@ k_composite_bwd(const CompositeArgs a) {
     fence_mbar_init();
   }
   for (int i = tid; i < B * STR; i += kCtaThreads) s_acc[i] = 0.f;
-  if (tid < B / 32) s_touched[tid] = 0u;
+  if (tid < B / 32) { s_touched[0][tid] = 0u; s_touched[1][tid] = 0u; }
   __syncthreads();
 
   // per-pixel registers
@@ -121,17 +187,13 @@ k_composite_bwd(const CompositeArgs a) {
     pixel_dir(pg.px, pg.py, c9, d);
     sh_basis<C>(d[0], d[1], d[2], Y);
   }
-  // ---- TBUF: this lane's column of the block's basis matrix, Ycol[p] = Y_k(pixel p), k = lane % KL
+  // ---- TBUF: per-warp transpose buffer.  Layout (floats): SH rows [G*3][32] (row = hit*3 + channel), geometry rows
+  // [G*6][32], then the block's basis matrix Ysm[k][36] (k-major, padded against bank conflicts)
   float* my_t = s_tbuf + warp * BT::kTbufFloats;
-  float Ycol[TBUF ? 32 : 1];
-  const int tk = lane & (BT::kKL - 1);   // k index served by this lane in the flush
-  const int tj = lane / BT::kKL;         // row group
+  float* my_y = my_t + BT::kG * 9 * 32;
   if constexpr (TBUF) {
 #pragma unroll
-    for (int k = 0; k < BT::kKL; ++k) my_t[lane * BT::kKL + k] = (k < CC) ? Y[k < CC ? k : 0] : 0.f;
-    __syncwarp();
-#pragma unroll
-    for (int p = 0; p < 32; ++p) Ycol[p] = my_t[p * BT::kKL + tk];
+    for (int k = 0; k < BT::kKL; ++k) my_y[k * 36 + lane] = (k < CC) ? Y[k < CC ? k : 0] : 0.f;
     __syncwarp();
   }
   int nslot = 0;            // hits buffered in my_t (warp-uniform)
@@ -143,33 +205,7 @@ k_composite_bwd(const CompositeArgs a) {
   // flush of the transpose buffer: rows [h][0..2] x basis -> SH gradients, rows [h][3..8] row sums -> geometry
   auto flush_tbuf = [&]() {
     if constexpr (TBUF) {
-      __syncwarp();
-      for (int row = tj; row < nslot * 3; row += BT::kJ) {
-        const int h = row / 3, c = row - 3 * h;
-        const float4* tp = reinterpret_cast<const float4*>(my_t + (h * 9 + c) * 32);
-        float acc = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 t = tp[q];
-          acc = fmaf(t.x, Ycol[4 * q], acc); acc = fmaf(t.y, Ycol[4 * q + 1], acc);
-          acc = fmaf(t.z, Ycol[4 * q + 2], acc); acc = fmaf(t.w, Ycol[4 * q + 3], acc);
-        }
-        const int jj = (slots >> (8 * h)) & 255u;
-        if (tk < CC) atomicAdd(s_acc + jj * STR + 6 + c * CC + tk, acc);
-      }
-      for (int r0 = 0; r0 < nslot * 6; r0 += 32) {
-        const int r = r0 + lane;
-        if (r < nslot * 6) {
-          const int h = r / 6, v = r - 6 * h;
-          const float* base = my_t + (h * 9 + 3 + v) * 32;
-          float s = 0.f;
-#pragma unroll
-          for (int p = 0; p < 32; ++p) s += base[(p + lane) & 31];
-          const int jj = (slots >> (8 * h)) & 255u;
-          atomicAdd(s_acc + jj * STR + v, s);
-        }
-      }
-      __syncwarp();
+      flush_tbuf_fn<PAY, C, EXTRAS>(my_t, my_y, s_acc, nslot, slots, lane);
       nslot = 0;
       slots = 0u;
     }
@@ -188,10 +224,15 @@ k_composite_bwd(const CompositeArgs a) {
   if (nb > 1) { int j = B + tid; id_next = (tid < B && j < n) ? ids[j] : 0; }
 
   bool warp_done = __all_sync(kFull, done);
+  cp_async_wait<0>();
+  if (PAY == PAY_SH && use_bulk) mbar_wait(&s_bar[0], 0u);
+  __syncthreads();
+  // two block barriers per batch: (B) accumulators complete -> flush; (C) batch retired + next batch landed + vote
   for (int b = 0; b < nb; ++b) {
     unsigned char* st = smem + (b & 1) * L::kBytes;
     const int cnt = min(B, n - b * B);
     const bool has_next = (b + 1 < nb);
+    unsigned* touched_now = s_touched[b & 1];
     if (has_next) {
       const int cntn = min(B, n - (b + 1) * B);
       uint64_t* barn = &s_bar[(b + 1) & 1];
@@ -200,12 +241,7 @@ k_composite_bwd(const CompositeArgs a) {
                                                 use_bulk, barn);
       else cp_async_commit();
       if (b + 2 < nb) { int j = (b + 2) * B + tid; id_next = (tid < B && j < n) ? ids[j] : 0; }
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
     }
-    if (PAY == PAY_SH && use_bulk) mbar_wait(&s_bar[b & 1], (uint32_t)((b >> 1) & 1));
-    __syncthreads();
 
     if (!warp_done) {
       const float4* sg0 = reinterpret_cast<const float4*>(st + L::kG0);
@@ -299,9 +335,10 @@ k_composite_bwd(const CompositeArgs a) {
             done = T < a.thresh;
           }
           if constexpr (TBUF) {
-            float* row = my_t + nslot * (9 * 32) + lane;
-            row[0] = t0; row[32] = t1; row[64] = t2;
-            row[96] = e0; row[128] = e1; row[160] = e2; row[192] = e3; row[224] = e4; row[256] = e5;
+            float* rs = my_t + nslot * (3 * 32) + lane;                    // SH rows of this hit
+            float* rg = my_t + (BT::kG * 3 + nslot * 6) * 32 + lane;       // geometry rows of this hit
+            rs[0] = t0; rs[32] = t1; rs[64] = t2;
+            rg[0] = e0; rg[32] = e1; rg[64] = e2; rg[96] = e3; rg[128] = e4; rg[160] = e5;
             slots |= (unsigned)jj << (8 * nslot);
             if (++nslot == BT::kG) flush_tbuf();
           } else {
@@ -316,64 +353,87 @@ k_composite_bwd(const CompositeArgs a) {
             }
           }
         }
-        if (touched && lane == 0) atomicOr(&s_touched[r], touched);
+        if (touched && lane == 0) atomicOr(&touched_now[r], touched);
         if (__all_sync(kFull, done)) { warp_done = true; break; }
       }
       if (nslot) flush_tbuf();  // the batch's staging buffer (and its entry indices) is about to be recycled
     }
     __syncthreads();
     // flush this batch's accumulators: one (Gaussian, tile) instance per thread
-    if (tid < cnt && ((s_touched[tid >> 5] >> (tid & 31)) & 1u)) {
+    if (tid < B / 32) s_touched[(b + 1) & 1][tid] = 0u;  // recycled for batch b+1 (last read before barrier C of b-1)
+    if (tid < cnt && ((touched_now[tid >> 5] >> (tid & 31)) & 1u)) {
       const int id = reinterpret_cast<const int*>(st + L::kIds)[tid];
       float* row = s_acc + tid * STR;
-      float g[STR];
-#pragma unroll
-      for (int k = 0; k < STR; k += 4) {
-        float4 q = *reinterpret_cast<float4*>(row + k);
-        g[k] = q.x; g[k + 1] = q.y; g[k + 2] = q.z; g[k + 3] = q.w;
-        *reinterpret_cast<float4*>(row + k) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      if constexpr (FUSED) {
-        float gd = 0.f;
-        if constexpr (PAY == PAY_RGB && EXTRAS) gd = g[9];
-        red_add_v4(a.ggeom + (size_t)id * 8, g[0], g[1], g[2], g[3]);
-        red_add_v4(a.ggeom + (size_t)id * 8 + 4, g[4], g[5], gd, 0.f);
-      } else {
-        red_add_v2(a.grad_mean + (size_t)id * 2, g[0], g[1]);
-        red_add_v4(a.grad_cov + (size_t)id * 4, g[2], g[3], g[3], g[4]);
-        red_add(a.grad_alpha + id, g[5]);
-      }
-      if constexpr (PAY == PAY_SH) {
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (TBUF) {
+        // [3*CC sh | 6 geometry]: streamed 16 bytes at a time (few live registers)
         float* dst = a.grad_pay + (size_t)id * (3 * CC);
         if ((3 * CC) % 4 == 0 && ((reinterpret_cast<uintptr_t>(a.grad_pay) & 15) == 0)) {
-#pragma unroll
-          for (int k = 0; k < 3 * CC; k += 4) red_add_v4(dst + k, g[6 + k], g[7 + k], g[8 + k], g[9 + k]);
+#pragma unroll 4
+          for (int k = 0; k < 3 * CC; k += 4) {
+            const float4 q = *reinterpret_cast<float4*>(row + k);
+            *reinterpret_cast<float4*>(row + k) = z4;
+            red_add_v4(dst + k, q.x, q.y, q.z, q.w);
+          }
         } else {
-#pragma unroll
-          for (int k = 0; k < 3 * CC; ++k) red_add(dst + k, g[6 + k]);
+#pragma unroll 3
+          for (int k = 0; k < 3 * CC; ++k) {
+            const float q = row[k];
+            row[k] = 0.f;
+            red_add(dst + k, q);
+          }
         }
-      } else if constexpr (PAY == PAY_RGB) {
+        float g[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { g[k] = row[BT::kGeoOff + k]; row[BT::kGeoOff + k] = 0.f; }
         if constexpr (FUSED) {
-          red_add_v4(a.gpay + (size_t)id * 4, g[6], g[7], g[8], 0.f);
+          red_add_v4(a.ggeom + (size_t)id * 8, g[0], g[1], g[2], g[3]);
+          red_add_v4(a.ggeom + (size_t)id * 8 + 4, g[4], g[5], 0.f, 0.f);
         } else {
-          red_add(a.grad_pay + (size_t)id * 3, g[6]);
-          red_add(a.grad_pay + (size_t)id * 3 + 1, g[7]);
-          red_add(a.grad_pay + (size_t)id * 3 + 2, g[8]);
+          red_add_v2(a.grad_mean + (size_t)id * 2, g[0], g[1]);
+          red_add_v4(a.grad_cov + (size_t)id * 4, g[2], g[3], g[3], g[4]);
+          red_add(a.grad_alpha + id, g[5]);
         }
       } else {
-        red_add(a.grad_pay + id, g[6]);
+        float g[STR];
+#pragma unroll
+        for (int k = 0; k < STR; k += 4) {
+          float4 q = *reinterpret_cast<float4*>(row + k);
+          g[k] = q.x; g[k + 1] = q.y; g[k + 2] = q.z; g[k + 3] = q.w;
+          *reinterpret_cast<float4*>(row + k) = z4;
+        }
+        if constexpr (FUSED) {
+          float gd = 0.f;
+          if constexpr (PAY == PAY_RGB && EXTRAS) gd = g[9];
+          red_add_v4(a.ggeom + (size_t)id * 8, g[0], g[1], g[2], g[3]);
+          red_add_v4(a.ggeom + (size_t)id * 8 + 4, g[4], g[5], gd, 0.f);
+        } else {
+          red_add_v2(a.grad_mean + (size_t)id * 2, g[0], g[1]);
+          red_add_v4(a.grad_cov + (size_t)id * 4, g[2], g[3], g[3], g[4]);
+          red_add(a.grad_alpha + id, g[5]);
+        }
+        if constexpr (PAY == PAY_SH) {  // C == 1: three coefficients
+          float* dst = a.grad_pay + (size_t)id * (3 * CC);
+#pragma unroll
+          for (int k = 0; k < 3 * CC; ++k) red_add(dst + k, g[6 + k]);
+        } else if constexpr (PAY == PAY_RGB) {
+          if constexpr (FUSED) {
+            red_add_v4(a.gpay + (size_t)id * 4, g[6], g[7], g[8], 0.f);
+          } else {
+            red_add(a.grad_pay + (size_t)id * 3, g[6]);
+            red_add(a.grad_pay + (size_t)id * 3 + 1, g[7]);
+            red_add(a.grad_pay + (size_t)id * 3 + 2, g[8]);
+          }
+        } else {
+          red_add(a.grad_pay + id, g[6]);
+        }
       }
     }
-    __syncthreads();
-    if (tid < B / 32) s_touched[tid] = 0u;
-    const int all_done = __syncthreads_and(warp_done ? 1 : 0);
-    if (all_done) {
-      if (has_next) {
-        cp_async_wait<0>();
-        if (PAY == PAY_SH && use_bulk) mbar_wait(&s_bar[(b + 1) & 1], (uint32_t)(((b + 1) >> 1) & 1));
-      }
-      break;
+    if (has_next) {
+      cp_async_wait<0>();
+      if (PAY == PAY_SH && use_bulk) mbar_wait(&s_bar[(b + 1) & 1], (uint32_t)(((b + 1) >> 1) & 1));
     }
+    if (__syncthreads_and(warp_done ? 1 : 0)) break;
   }
 
   if (PAY == PAY_RGB && a.g_bg && pg.inside) {  // gs/renderer.py:1282 nan_to_num(grad * T)

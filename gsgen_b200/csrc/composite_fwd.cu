@@ -98,6 +98,12 @@ k_composite_fwd(const CompositeArgs a) {
   if (nb > 1) { int j = B + tid; id_next = (tid < B && j < n) ? ids[j] : 0; }
 
   bool warp_done = __all_sync(kFull, done);
+  // batch 0 has landed for everyone
+  cp_async_wait<0>();
+  if (PAY == PAY_SH && use_bulk) mbar_wait(&s_bar[0], 0u);
+  __syncthreads();
+  // ONE block barrier per batch: the copies of batch b+1 are issued before batch b is composited and waited
+  // for right before the barrier that also retires batch b's buffer and votes on early termination.
   for (int b = 0; b < nb; ++b) {
     unsigned char* st = smem + (b & 1) * L::kBytes;
     const int cnt = min(B, n - b * B);
@@ -111,12 +117,7 @@ k_composite_fwd(const CompositeArgs a) {
       else cp_async_commit();
       staged += cntn;
       if (b + 2 < nb) { int j = (b + 2) * B + tid; id_next = (tid < B && j < n) ? ids[j] : 0; }
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
     }
-    if (PAY == PAY_SH && use_bulk) mbar_wait(&s_bar[b & 1], (uint32_t)((b >> 1) & 1));
-    __syncthreads();
 
     if (!warp_done) {
       const float4* sg0 = reinterpret_cast<const float4*>(st + L::kG0);
@@ -177,14 +178,11 @@ k_composite_fwd(const CompositeArgs a) {
         if (__all_sync(kFull, done)) { warp_done = true; break; }
       }
     }
-    const int all_done = __syncthreads_and(warp_done ? 1 : 0);
-    if (all_done) {
-      if (has_next) {  // drain the copies already in flight before the CTA retires its shared memory
-        cp_async_wait<0>();
-        if (PAY == PAY_SH && use_bulk) mbar_wait(&s_bar[(b + 1) & 1], (uint32_t)(((b + 1) >> 1) & 1));
-      }
-      break;
+    if (has_next) {  // batch b+1 must have landed (also drains the copies before the CTA may retire)
+      cp_async_wait<0>();
+      if (PAY == PAY_SH && use_bulk) mbar_wait(&s_bar[(b + 1) & 1], (uint32_t)(((b + 1) >> 1) & 1));
     }
+    if (__syncthreads_and(warp_done ? 1 : 0)) break;
   }
 
   if (a.stats) {  // D_eff bookkeeping for the roofline report; not on the default path
