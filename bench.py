@@ -29,6 +29,36 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+
+def usable_cpus() -> int:
+    """CPUs this container may actually use: min(affinity, cgroup quota).  The GPU boxes show 128 cores but carry a
+    CFS quota (cpu.max 1600000/100000 = 16 CPUs, measured round 1); threads beyond the quota only get the whole
+    process throttled in 100 ms slices -- which showed up as random 100-250 ms stalls in the timed loop."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return n
+
+
+_IS_REFERENCE_ARM = any(a == "reference" or a == "--impl=reference" for a in sys.argv[1:])
+if _IS_REFERENCE_ARM:
+    os.environ.setdefault("OMP_NUM_THREADS", str(usable_cpus()))
+else:
+    # the GPU arm's host work is a few tiny CPU tensor ops per view: an OpenMP pool of 64 spinning workers would
+    # only burn the container's CPU quota
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("MKL_NUM_THREADS", "1")
+
 import torch  # noqa: E402
 
 METRIC = "fwd+bwd Gaussians*pixels/s"
@@ -46,6 +76,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--svec-scale", type=float, default=1.0, help="C5 tile-occupancy sweep")
+    ap.add_argument("--clock-period", type=float, default=0.1, help="NVML sampling period in s (0 = off)")
     return ap.parse_args()
 
 
@@ -144,7 +175,7 @@ class ClockSampler:
         reasons = sorted(n for b, n in self.REASONS.items() if mask & b)
         return {"sm_mhz": statistics.median(x[0] for x in win), "sm_max_mhz": self.sm_max,
                 "power_w_max": max(x[1] for x in win), "samples": len(win), "reasons": reasons,
-                "source": "NVML (pynvml), 10 ms period, window = timed region"}
+                "source": "NVML (pynvml), %g s period, window = timed region" % self.period}
 
 
 def measured_peaks():
@@ -220,27 +251,21 @@ def cpu_step_factory(workload, scene, cam, c2w, window_frac=1.0):
     return step, px
 
 
-def run_cpu_baseline(workload, scene, cam, c2w, budget_s=30.0):
-    """Oracle timed on the host cores on a bounded sample (about <= budget_s of CPU work)."""
-    import oracle
-
-    oracle.build()
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    N0 = scene.N
-    # probe with a 1/16 window, then size the sample
-    step, px = cpu_step_factory(workload, scene, cam, c2w, 1.0 / 16)
-    t0 = time.perf_counter(); step(); t_probe = time.perf_counter() - t0
-    frac = 1.0 if t_probe * 16 <= budget_s else (0.25 if t_probe * 4 <= budget_s else 1.0 / 16)
-    if frac != 1.0 / 16:
-        step, px = cpu_step_factory(workload, scene, cam, c2w, frac)
-        t0 = time.perf_counter(); step(); t = time.perf_counter() - t0
-    else:
-        t = t_probe
-    return {"value": N0 * px / t, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"1 step (fwd+bwd, all {N0} Gaussians preprocessed and binned) compositing a centred window of "
-                      f"{frac:.4g} of the tiles = {px} pixels, {t:.2f} s; OpenMP + torch threads = {threads}",
-            "seconds": t}
+def run_cpu_baseline(args):
+    """cpu_baseline leg: the oracle (CPU restatement of the reference path) timed on the host cores, in a child
+    process so that it gets its own OpenMP pool sized to the usable CPUs (the GPU arm runs single-threaded)."""
+    n = usable_cpus()
+    env = dict(os.environ, OMP_NUM_THREADS=str(n), MKL_NUM_THREADS=str(n), CUDA_VISIBLE_DEVICES="")
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", "1",
+           "--warmup", "0", "--svec-scale", str(args.svec_scale)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    if not line:
+        raise RuntimeError("reference arm printed no JSON: " + out.stderr[-300:])
+    d = json.loads(line[-1])
+    cb = d["cpu_baseline"]
+    cb["seconds_per_step"] = d["ms_per_step"] / 1e3
+    return cb
 
 
 def run_reference_arm(args):
@@ -252,7 +277,7 @@ def run_reference_arm(args):
     from gsgen_b200.scenes import make_scene
 
     oracle.build()
-    threads = os.cpu_count() or 1
+    threads = int(os.environ.get("OMP_NUM_THREADS", usable_cpus()))
     torch.set_num_threads(threads)
     wl = args.workload
     scene = make_scene(wl, svec_scale=args.svec_scale)
@@ -349,12 +374,18 @@ def run_ours(args):
 
     # ---- warm-up (clock sampler already running)
     sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
-    if rank == 0:
+                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]), args.clock_period)
+    if rank == 0 and args.clock_period > 0:
         sampler.start()
+        time.sleep(0.5)
     for _ in range(max(3, args.warmup)):
         step()
-    torch.cuda.synchronize()
+    # ... plus >= 1.5 s of extra untimed steps: the first backward spawns autograd / CUDA helper threads and the
+    # container's CPU quota needs a few periods to settle (measured: sporadic 100-250 ms host stalls otherwise)
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 1.5:
+        step()
+        torch.cuda.synchronize()
     ctxs = [_lib.ctx(dev, s) for s in slot_of.values()]
     hm = (ctypes.c_float * 6)()
     hc = (ctypes.c_int64 * 5)()
@@ -469,7 +500,7 @@ def run_ours(args):
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            cpu_base = run_cpu_baseline(wl, scene, cams[0], c2ws_cpu[0])
+            cpu_base = run_cpu_baseline(args)
         except Exception as e:  # the bench line must still print
             cpu_base = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     value = n_views * scene.N * H * W / (ms_max / 1e3)

@@ -41,8 +41,9 @@ k_gather_counts(uint32_t N, const int32_t* __restrict__ perm, const int32_t* __r
   count_sorted[j] = count[perm[j]];
 }
 
-// One warp expands 32 consecutive Gaussians (in depth order) cooperatively: for each Gaussian with duplicates the
-// 32 lanes write its (tile, id) pairs to consecutive slots (coalesced stores).
+// One warp expands 32 consecutive Gaussians (in depth order).  Their duplicate slots form ONE contiguous range of the
+// output; the lanes walk that range 32 slots at a time (fully coalesced stores) and find the owner of each slot with a
+// 5-step binary search over the 32 per-lane start offsets (register shuffles).
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
 k_emit_tiles(uint32_t N, const int32_t* __restrict__ perm, const int32_t* __restrict__ count_sorted,
@@ -53,33 +54,45 @@ k_emit_tiles(uint32_t N, const int32_t* __restrict__ perm, const int32_t* __rest
   const uint32_t base = warp_global * 32;
   if (base >= N) return;
   const uint32_t j = base + lane;
-  int c = 0, off = 0, gid = 0;
+  int c = 0, incl = 0, gid = 0;
   ushort4 r = make_ushort4(0, 0, 0, 0);
   if (j < N) {
     c = count_sorted[j];
+    incl = incl_sorted[j];
     if (c > 0) {
-      off = incl_sorted[j] - c;
       gid = perm[j];
       r = rect[gid];
     }
   }
-  uint32_t have = __ballot_sync(0xffffffffu, c > 0);
-  while (have) {
-    int g = __ffs(have) - 1;
-    have &= have - 1;
-    int og = __shfl_sync(0xffffffffu, off, g);
-    int idg = __shfl_sync(0xffffffffu, gid, g);
-    int x0 = __shfl_sync(0xffffffffu, (int)r.x, g), y0 = __shfl_sync(0xffffffffu, (int)r.y, g);
-    int x1 = __shfl_sync(0xffffffffu, (int)r.z, g), y1 = __shfl_sync(0xffffffffu, (int)r.w, g);
-    const int w = x1 - x0 + 1;
-    // row by row: no integer division, slots of a row are consecutive
-    for (int ty = y0; ty <= y1; ++ty) {
-      const int row_slot = og + (ty - y0) * w;
-      const int row_tile = ty * tiles_w + x0;
-      for (int x = lane; x < w; x += 32) {
-        keys[row_slot + x] = (KeyT)(row_tile + x);
-        vals[row_slot + x] = idg;
-      }
+  // lanes past N inherit the last inclusive offset (zero-length ranges)
+  const uint32_t valid = __ballot_sync(0xffffffffu, j < N);
+  const int last = 31 - __clz(valid);
+  const int incl_last = __shfl_sync(0xffffffffu, incl, last);
+  if (j >= N) incl = incl_last;
+  const int excl = incl - c;                                   // this Gaussian's first slot
+  const int first = __shfl_sync(0xffffffffu, excl, 0);          // warp's first slot
+  const int total = incl_last - first;                          // slots owned by the warp
+  const int x0w = (int)r.x | ((int)r.y << 16);                  // packed for the shuffles
+  const int wq = (int)r.z - (int)r.x + 1;
+  for (int s0 = 0; s0 < total; s0 += 32) {  // warp-uniform trip count: every lane takes part in the shuffles
+    const int slot = first + s0 + lane;
+    // owner = max{ lane : excl_lane <= slot }  (a zero-count lane is shadowed by its successor with the same excl)
+    int pos = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      const int cand = pos + step;  // <= 31
+      const int e = __shfl_sync(0xffffffffu, excl, cand);
+      if (e <= slot) pos = cand;
+    }
+    const int eg = __shfl_sync(0xffffffffu, excl, pos);
+    const int idg = __shfl_sync(0xffffffffu, gid, pos);
+    const int xy = __shfl_sync(0xffffffffu, x0w, pos);
+    const int w = __shfl_sync(0xffffffffu, wq, pos);
+    if (s0 + lane < total) {
+      const int k = slot - eg;
+      const int ty = (xy >> 16) + k / w, tx = (xy & 0xffff) + k % w;
+      keys[slot] = (KeyT)(ty * tiles_w + tx);
+      vals[slot] = idg;
     }
   }
 }
