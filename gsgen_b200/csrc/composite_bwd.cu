@@ -39,7 +39,7 @@ template <int PAY, int C, bool EXTRAS> struct BwdTraits {
   static constexpr int kG = 4;                                   // hits per flush
   static constexpr int kKL = CC <= 4 ? 4 : 16;                   // lanes along k (power of two >= CC)
   static constexpr int kJ = 32 / kKL;                            // row groups
-  static constexpr int kYsmFloats = kTbuf ? kKL * 36 : 0;        // per warp: basis matrix [k][36] (k-major, padded)
+  static constexpr int kYsmFloats = kTbuf ? kKL * 32 : 0;        // per warp: basis matrix [k][32 px], float4 groups rotated by k
   static constexpr int kTbufFloats = kTbuf ? kG * 9 * 32 + kYsmFloats : 0;  // per warp
   static constexpr int kNR = (3 * kG + kJ - 1) / kJ;             // SH rows per lane group in a flush
   // accumulator row layout: butterfly path [6 geometry | payload]; transpose-buffer path [3*CC sh | 6 geometry]
@@ -72,10 +72,10 @@ GSB_FLUSH_ATTR void flush_tbuf_fn(const float* my_t, const float* my_y, float* s
 #pragma unroll
   for (int i = 0; i < BT::kNR; ++i) acc[i] = 0.f;
   const float* trow = my_t + tj * 32;
-  const float* yrow = my_y + tk * 36;
+  const float* yrow = my_y + tk * 32;
 #pragma unroll 2
   for (int q = 0; q < 8; ++q) {
-    const float4 y4 = *reinterpret_cast<const float4*>(yrow + 4 * q);
+    const float4 y4 = *reinterpret_cast<const float4*>(yrow + 4 * ((q + tk) & 7));
 #pragma unroll
     for (int i = 0; i < BT::kNR; ++i) {
       const float4 t = *reinterpret_cast<const float4*>(trow + i * (BT::kJ * 32) + 4 * q);
@@ -108,8 +108,11 @@ GSB_FLUSH_ATTR void flush_tbuf_fn(const float* my_t, const float* my_y, float* s
   __syncwarp();
 }
 
+#ifndef GSB_BWD_B
+#define GSB_BWD_B 32  // list entries per staged batch for SH degree >= 2 (shared memory: 3 CTAs/SM at 32)
+#endif
 #ifndef GSB_BWD_MINBLOCKS
-#define GSB_BWD_MINBLOCKS 2  // 2 CTAs/SM (<=128 registers); measured against 1 (162 registers, no spills) in round 1
+#define GSB_BWD_MINBLOCKS 3  // CTAs/SM the register allocation is capped for (3 -> 80 registers, 56 B of spills at SH deg 3)
 #endif
 
 template <int PAY, int C, bool EXTRAS, bool FUSED, int B>
@@ -188,12 +191,13 @@ k_composite_bwd(const CompositeArgs a) {
     sh_basis<C>(d[0], d[1], d[2], Y);
   }
   // ---- TBUF: per-warp transpose buffer.  Layout (floats): SH rows [G*3][32] (row = hit*3 + channel), geometry rows
-  // [G*6][32], then the block's basis matrix Ysm[k][36] (k-major, padded against bank conflicts)
+  // [G*6][32], then the block's basis matrix Ysm[k][32] (k-major, 16-byte groups rotated by k against bank conflicts)
   float* my_t = s_tbuf + warp * BT::kTbufFloats;
   float* my_y = my_t + BT::kG * 9 * 32;
   if constexpr (TBUF) {
 #pragma unroll
-    for (int k = 0; k < BT::kKL; ++k) my_y[k * 36 + lane] = (k < CC) ? Y[k < CC ? k : 0] : 0.f;
+    for (int k = 0; k < BT::kKL; ++k)  // pixel `lane` sits in float4 group lane/4, rotated by k (bank-conflict free)
+      my_y[k * 32 + (((lane >> 2) + k) & 7) * 4 + (lane & 3)] = (k < CC) ? Y[k < CC ? k : 0] : 0.f;
     __syncwarp();
   }
   int nslot = 0;            // hits buffered in my_t (warp-uniform)
@@ -476,8 +480,8 @@ int launch_composite_bwd(int pay_kind, int C, bool extras, bool fused, const Com
       switch (C) {
         case 1: return fused ? launch_one<PAY_SH, 1, false, true, 256>(a, st) : launch_one<PAY_SH, 1, false, false, 256>(a, st);
         case 2: return fused ? launch_one<PAY_SH, 2, false, true, 128>(a, st) : launch_one<PAY_SH, 2, false, false, 128>(a, st);
-        case 3: return fused ? launch_one<PAY_SH, 3, false, true, 64>(a, st) : launch_one<PAY_SH, 3, false, false, 64>(a, st);
-        case 4: return fused ? launch_one<PAY_SH, 4, false, true, 64>(a, st) : launch_one<PAY_SH, 4, false, false, 64>(a, st);
+        case 3: return fused ? launch_one<PAY_SH, 3, false, true, GSB_BWD_B>(a, st) : launch_one<PAY_SH, 3, false, false, GSB_BWD_B>(a, st);
+        case 4: return fused ? launch_one<PAY_SH, 4, false, true, GSB_BWD_B>(a, st) : launch_one<PAY_SH, 4, false, false, GSB_BWD_B>(a, st);
         default: break;
       }
     default: break;
