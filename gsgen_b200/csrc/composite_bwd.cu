@@ -68,9 +68,9 @@ GSB_FLUSH_ATTR void flush_tbuf_fn(const float* my_t, const float* my_y, float* s
   const int tk = lane & (BT::kKL - 1);
   const int tj = lane / BT::kKL;
   __syncwarp();
-  float acc[BT::kNR];
+  float acc[BT::kNR], aco[BT::kNR];  // even / odd pixel partial sums (FFMA2)
 #pragma unroll
-  for (int i = 0; i < BT::kNR; ++i) acc[i] = 0.f;
+  for (int i = 0; i < BT::kNR; ++i) { acc[i] = 0.f; aco[i] = 0.f; }
   const float* trow = my_t + tj * 32;
   const float* yrow = my_y + tk * 32;
 #pragma unroll 2
@@ -79,8 +79,8 @@ GSB_FLUSH_ATTR void flush_tbuf_fn(const float* my_t, const float* my_y, float* s
 #pragma unroll
     for (int i = 0; i < BT::kNR; ++i) {
       const float4 t = *reinterpret_cast<const float4*>(trow + i * (BT::kJ * 32) + 4 * q);
-      acc[i] = fmaf(t.x, y4.x, acc[i]); acc[i] = fmaf(t.y, y4.y, acc[i]);
-      acc[i] = fmaf(t.z, y4.z, acc[i]); acc[i] = fmaf(t.w, y4.w, acc[i]);
+      ffma2(acc[i], aco[i], t.x, t.y, y4.x, y4.y);
+      ffma2(acc[i], aco[i], t.z, t.w, y4.z, y4.w);
     }
   }
 #pragma unroll
@@ -89,7 +89,7 @@ GSB_FLUSH_ATTR void flush_tbuf_fn(const float* my_t, const float* my_y, float* s
     if (row < nslot * 3 && tk < CC) {
       const int h = row / 3, c = row - 3 * h;
       const int jj = (slots >> (8 * h)) & 255u;
-      atomicAdd(s_acc + jj * STR + BT::kPayOff + c * CC + tk, acc[i]);
+      atomicAdd(s_acc + jj * STR + BT::kPayOff + c * CC + tk, acc[i] + aco[i]);
     }
   }
   // geometry: plain row sums, one row per lane (rotated 16-byte reads: conflict-free)
@@ -283,12 +283,14 @@ k_composite_bwd(const CompositeArgs a) {
               float s = 0.f;
               if constexpr (CC % 4 == 0) {
                 const float4* p4 = reinterpret_cast<const float4*>(shp + c * CC);
+                float se = 0.f, so = 0.f;  // even / odd k partial sums: one FFMA2 per coefficient pair
 #pragma unroll
                 for (int k = 0; k < CC / 4; ++k) {
                   float4 q = p4[k];
-                  s = fmaf(q.x, Y[4 * k], s); s = fmaf(q.y, Y[4 * k + 1], s);
-                  s = fmaf(q.z, Y[4 * k + 2], s); s = fmaf(q.w, Y[4 * k + 3], s);
+                  ffma2(se, so, q.x, q.y, Y[4 * k], Y[4 * k + 1]);
+                  ffma2(se, so, q.z, q.w, Y[4 * k + 2], Y[4 * k + 3]);
                 }
+                s = se + so;
               } else {
 #pragma unroll
                 for (int k = 0; k < CC; ++k) s = fmaf(shp[c * CC + k], Y[k], s);

@@ -143,12 +143,14 @@ k_composite_fwd(const CompositeArgs a) {
               float s = 0.f;
               if constexpr (CC % 4 == 0) {
                 const float4* p4 = reinterpret_cast<const float4*>(shp + c * CC);
+                float se = 0.f, so = 0.f;  // even / odd k partial sums: one FFMA2 per coefficient pair
 #pragma unroll
                 for (int k = 0; k < CC / 4; ++k) {
                   float4 q = p4[k];
-                  s = fmaf(q.x, Y[4 * k], s); s = fmaf(q.y, Y[4 * k + 1], s);
-                  s = fmaf(q.z, Y[4 * k + 2], s); s = fmaf(q.w, Y[4 * k + 3], s);
+                  ffma2(se, so, q.x, q.y, Y[4 * k], Y[4 * k + 1]);
+                  ffma2(se, so, q.z, q.w, Y[4 * k + 2], Y[4 * k + 3]);
                 }
+                s = se + so;
               } else {
 #pragma unroll
                 for (int k = 0; k < CC; ++k) s = fmaf(shp[c * CC + k], Y[k], s);

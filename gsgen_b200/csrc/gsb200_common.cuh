@@ -163,6 +163,18 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
   return y;
 }
+// Packed FP32x2 FMA (Blackwell FFMA2, PTX fma.rn.f32x2): (dx,dy) += (ax,ay)*(bx,by) in ONE issue slot.  Measured on
+// B200 (tools/microbench/ffma2.cu): the FMA pipe still retires 128 lane-FMAs/clk/SM, but an FFMA2 costs one issue
+// slot for two FMAs -- and these kernels are issue-slot bound (LDS / MUFU / ALU compete with the FMAs).
+__device__ __forceinline__ void ffma2(float& dx, float& dy, float ax, float ay, float bx, float by) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(ax), "f"(ay));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(bx), "f"(by));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(dx), "f"(dy));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(dx), "=f"(dy) : "l"(rd));
+}
+
 // sigmoid as the reference's 1/(1+expf(-x)) (shencoder.h:4), MUFU ex2 + rcp
 __device__ __forceinline__ float sigmoid_fast(float x) {
   return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
