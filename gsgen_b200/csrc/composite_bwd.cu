@@ -256,11 +256,15 @@ k_composite_bwd(const CompositeArgs a) {
         if (j < cnt) hit = splat_hits_block(sg0[j], sg1[j], pg);
         unsigned m = __ballot_sync(kFull, hit);
         unsigned touched = 0u;
+        // software pipeline over the hits: the next hit's record is fetched while the current one is evaluated
+        int bitn = __ffs(m) - 1;
+        float4 n0 = sg0[m ? r * 32 + bitn : 0], n1 = sg1[m ? r * 32 + bitn : 0];
         while (m) {
-          const int bit = __ffs(m) - 1;
+          const int bit = bitn;
           const int jj = r * 32 + bit;
+          const float4 g0 = n0, g1 = n1;
           m &= m - 1;
-          const float4 g0 = sg0[jj], g1 = sg1[jj];
+          if (m) { bitn = __ffs(m) - 1; n0 = sg0[r * 32 + bitn]; n1 = sg1[r * 32 + bitn]; }
           float G, u, v;
           const float aG = splat_aG(g0, g1, pg.px, pg.py, &G, &u, &v);
           const bool ok = !done && (aG >= kMinRenderAlpha);
