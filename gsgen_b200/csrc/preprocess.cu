@@ -31,14 +31,11 @@ __global__ void __launch_bounds__(kThreads)
 k_cull_bsphere(uint32_t N, const float* __restrict__ mean, const float* __restrict__ svec,
                const float* __restrict__ normal, const float* __restrict__ pts, uint8_t* __restrict__ mask,
                float thresh) {
-  __shared__ float s_n[18], s_p[18];
-  if (threadIdx.x < 18) { s_n[threadIdx.x] = normal[threadIdx.x]; s_p[threadIdx.x] = pts[threadIdx.x]; }
-  __syncthreads();
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   float m[3] = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2]};
   float r = fmaxf(fmaxf(svec[3 * i], svec[3 * i + 1]), svec[3 * i + 2]) * thresh;
-  mask[i] = sphere_in_frustum(m, r, s_n, s_p) ? 1 : 0;
+  mask[i] = sphere_in_frustum(m, r, normal, pts) ? 1 : 0;  // plane data: uniform read-only loads (L1 broadcast)
 }
 
 __global__ void __launch_bounds__(kThreads)
