@@ -341,7 +341,10 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # a mismatched collective must fail fast, not burn GPU time until the default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     wl = args.workload
     C = SH_C[wl]
     scene = make_scene(wl, svec_scale=args.svec_scale)
@@ -380,12 +383,21 @@ def run_ours(args):
         time.sleep(0.5)
     for _ in range(max(3, args.warmup)):
         step()
-    # ... plus >= 1.5 s of extra untimed steps: the first backward spawns autograd / CUDA helper threads and the
-    # container's CPU quota needs a few periods to settle (measured: sporadic 100-250 ms host stalls otherwise)
+    # ... plus ~1.5 s of extra untimed steps: the first backward spawns autograd / CUDA helper threads and the
+    # container's CPU quota needs a few periods to settle (measured: sporadic 100-250 ms host stalls otherwise).
+    # The COUNT is agreed across ranks (every step contains a collective): max over ranks of a 5-step estimate.
+    torch.cuda.synchronize()
     t_w = time.perf_counter()
-    while time.perf_counter() - t_w < 1.5:
+    for _ in range(5):
         step()
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    est = torch.tensor([(time.perf_counter() - t_w) / 5], device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    n_extra = int(min(1000, max(10, 1.5 / max(float(est.item()), 1e-4))))
+    for _ in range(n_extra):
+        step()
+    torch.cuda.synchronize()
     ctxs = [_lib.ctx(dev, s) for s in slot_of.values()]
     hm = (ctypes.c_float * 6)()
     hc = (ctypes.c_int64 * 5)()
@@ -509,7 +521,8 @@ def run_ours(args):
         except Exception as e:  # the bench line must still print
             cpu_base = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     value = n_views * scene.N * H * W / (ms_max / 1e3)
-    my_kernels_per_view = 9  # preprocess, total_from_scan, fill x2, emit_keys, tile_ranges, composite_fwd/bwd, project_bwd
+    # preprocess, depth_keys, gather_counts, fill x2, emit_tiles, tile_ranges, composite_fwd, composite_bwd, project_bwd
+    my_kernels_per_view = 10
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong" if wl == "c4" else "weak",
@@ -517,12 +530,13 @@ def run_ours(args):
         "config": {"workload": workload_name(wl, scene, cams[0]), "views_per_step": n_views,
                    "views_per_gpu": len(mine), "parallelism": f"view-dp{world}",
                    "grad_allreduce_bytes": vpr.grad_bytes() if world > 1 else 0,
-                   "l2": "no explicit flush: per-step working set (236 B/Gaussian parameters + gradients + "
-                         "%.0f MB of keys/ids) exceeds the 126 MB L2" % (D * 24 / 1e6)},
+                   "l2": "no explicit flush: inputs larger than L2 -- per step %.0f MB of Gaussian parameters + as many "
+                         "gradients + %.0f MB of sort keys/ids stream through the 126 MB L2"
+                         % (vpr.grad_bytes() / 1e6, D * 12 / 1e6)},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": my_kernels_per_view * len(mine) * args.steps,
-        "library_launches_note": "plus cub::DeviceScan (2) and cub::DeviceRadixSort onesweep (~8) and 1-2 memsets per view",
+        "library_launches_note": "plus cub::DeviceScan (2 kernels), 2x cub::DeviceRadixSort onesweep (6 + 4 kernels) and 2 memsets per view",
         "roofline": roofline,
         "stages": stages,
         "ms_per_step_with_stage_events": ms_profiled,
