@@ -229,6 +229,8 @@ def cpu_step_factory(workload, scene, cam, c2w, window_frac=1.0):
     keep_flat = keep.view(-1)
 
     def step():
+        """-> (seconds in the per-Gaussian + binning stages incl. their backward, seconds in the window composite fwd+bwd)"""
+        t0 = time.perf_counter()
         mean = scene.mean.clone().requires_grad_()
         qvec = scene.qvec.clone().requires_grad_()
         svec = scene.svec.clone().requires_grad_()
@@ -244,9 +246,18 @@ def cpu_step_factory(workload, scene, cam, c2w, window_frac=1.0):
             start = torch.where(keep_flat, start, torch.full_like(start, -1))
             end = torch.where(keep_flat, end, torch.full_like(end, -1))
         topleft = torch.tensor([-cam.cx / cam.fx, -cam.cy / cam.fy], dtype=torch.float32)
-        rgb = oracle.render_sh(m2, c2, sh[mask].contiguous(), a, start, end, ids, topleft, c2w, C, cfg, None)
+        shm = sh[mask].contiguous()
+        # composite forward + backward on detached leaves (timed separately), then the chain rule through the
+        # per-Gaussian stages with the gradients it produced
+        m2d, c2d = m2.detach().requires_grad_(), c2.detach().requires_grad_()
+        shd, ad = shm.detach().requires_grad_(), a.detach().requires_grad_()
+        t1 = time.perf_counter()
+        rgb = oracle.render_sh(m2d, c2d, shd, ad, start, end, ids, topleft, c2w, C, cfg, None)
         rgb.backward(gradient=gout)
-        return D
+        t2 = time.perf_counter()
+        torch.autograd.backward([m2, c2, shm, a], [m2d.grad, c2d.grad, shd.grad, ad.grad])
+        t3 = time.perf_counter()
+        return (t1 - t0) + (t3 - t2), (t2 - t1)
 
     return step, px
 
@@ -283,28 +294,39 @@ def run_reference_arm(args):
     scene = make_scene(wl, svec_scale=args.svec_scale)
     cams, c2ws = make_views(wl, scene, 1)
     cam, c2w = cams[0], c2ws[0]
-    # bounded sample: size the tile window so that warmup+steps finish within ~3 minutes
-    step, px = cpu_step_factory(wl, scene, cam, c2w, 1.0 / 16)
-    t0 = time.perf_counter(); step(); t_probe = time.perf_counter() - t0
+    # bounded sample.  The per-Gaussian stages (project, 5M-key sort, their backward) do not shrink with a tile window,
+    # so a windowed step would understate the reference if its time were divided by the window's pixels only.  Rule:
+    # composite the FULL image whenever K+W such steps fit in ~4 minutes (16 usable cores: ~2.1 s/step); otherwise
+    # composite a centred window of fraction f and report value = N*H*W / (t_per_gaussian + t_composite / f), i.e. the
+    # composite time extrapolated to the whole image.
     total = args.steps + args.warmup
-    frac = 1.0 / 16
-    for f in (1.0, 0.25):
-        if t_probe * (16 * f) * total * 0.6 < 180.0:  # composite scales ~linearly with the window
+    step, px = cpu_step_factory(wl, scene, cam, c2w, 1.0)
+    tp, tc = step()
+    frac = 1.0
+    if (tp + tc) * total > 240.0:
+        for f in (0.25, 1.0 / 16):
             frac = f
-            break
-    step, px = cpu_step_factory(wl, scene, cam, c2w, frac)
+            if (tp + tc * f) * total <= 240.0:
+                break
+        step, px = cpu_step_factory(wl, scene, cam, c2w, frac)
     for _ in range(args.warmup):
         step()
+    acc_p = acc_c = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        a_, b_ = step()
+        acc_p += a_
+        acc_c += b_
     dt = (time.perf_counter() - t0) / args.steps
-    val = scene.N * px / dt
-    sample = (f"each step = full per-Gaussian stages on {scene.N} Gaussians + SH composite fwd+bwd on a centred window "
-              f"of {frac:.4g} of the tiles ({px} px); value = N*px/t")
+    H, W = cam.h, cam.w
+    t_full = acc_p / args.steps + (acc_c / args.steps) / frac
+    val = scene.N * H * W / t_full
+    sample = (f"each step = all per-Gaussian stages + binning on {scene.N} Gaussians (fwd+bwd) + SH composite fwd+bwd "
+              f"on a centred window of {frac:.4g} of the tiles ({px} px); measured {dt:.3f} s/step of which "
+              f"{acc_c / args.steps:.3f} s composite; value = N*H*W / (t_per_gaussian + t_composite/{frac:.4g})")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(wl, scene, cam), "views_per_step": 1, "parallelism": "cpu-openmp"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -490,20 +512,24 @@ def run_ours(args):
 
         for _ in range(3):
             e2e_step()
-        barrier(); torch.cuda.synchronize()
-        e0.record()
-        for _ in range(args.steps):
-            e2e_step()
-        e1.record()
-        torch.cuda.synchronize(); barrier()
-        t2 = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_runs = []
+        for _ in range(3):  # best of three K-step loops, like the device-resident number (host CFS throttling)
+            barrier(); torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.steps):
+                e2e_step()
+            e1.record()
+            torch.cuda.synchronize(); barrier()
+            t2 = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+            if world > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            e2e_runs.append(float(t2.item()))
+        t2 = torch.tensor([min(e2e_runs)])
         ms_e2e = float(t2.item())
         bi = len(mine) * (h_gout.numel() * 4 + 240)  # gradient image + the by-value camera struct
         bo = len(mine) * h_rgb.numel() * 4
         e2e = {"value": n_views * scene.N * H * W / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
+               "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo, "ms_per_step_all_runs": e2e_runs,
                "what": "render_view()+backward through the public API; per step: host camera pose (by-value kernel "
                        "argument) + pinned upstream gradient image H2D, rendered image D2H to pinned memory; Gaussian "
                        "parameters stay resident (they are the model state, like weights)"}
