@@ -46,7 +46,11 @@ class Gsb200ViewIn(ctypes.Structure):
         ("C", c_i32),
         ("sh_c2w9", c_f32 * 9),
         ("bg", c_void), ("bg_rgb", c_void),
+        ("act", c_i32),
     ]
+
+
+ACT_SVEC_EXP, ACT_ALPHA_SIGMOID, ACT_COLOR_SIGMOID = 1, 2, 4  # GSB200_ACT_* (include/gsb200.h)
 
 
 class Gsb200ViewOut(ctypes.Structure):

@@ -338,6 +338,7 @@ int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb
   const bool is_sh = in->sh != nullptr;
   GSB_CHECK(is_sh || in->color, GSB200_ERR_INVALID, "render_forward: need color or sh");
   GSB_CHECK(!is_sh || (in->C >= 1 && in->C <= 4), GSB200_ERR_UNSUPPORTED, "SH C=%d unsupported", in->C);
+  GSB_CHECK((in->act & ~7) == 0, GSB200_ERR_INVALID, "render_forward: unknown activation bits 0x%x", in->act);
   const bool extras = !is_sh && out->depth && out->opacity && out->z2;
   GSB_CHECK(is_sh || extras || (!out->depth && !out->opacity && !out->z2), GSB200_ERR_INVALID,
             "render_forward: depth / opacity / z2 must be given together");
@@ -359,7 +360,7 @@ int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb
     if ((rc = ctx->rect.reserve((size_t)N * 8))) return rc;
     if ((rc = ctx->count.reserve((size_t)N * 4))) return rc;
     if ((rc = begin_total(ctx, st))) return rc;
-    if ((rc = launch_preprocess(N, in->mean, in->qvec, in->svec, in->alpha, is_sh ? nullptr : in->color, cam,
+    if ((rc = launch_preprocess(N, in->mean, in->qvec, in->svec, in->alpha, is_sh ? nullptr : in->color, in->act, cam,
                                 out->mean2d, out->cov2d, out->depthg, out->mask, out->radii2d,
                                 ctx->splat.as<Splat>(), ctx->pay.as<float4>(), ctx->rect.as<ushort4>(),
                                 ctx->count.as<int32_t>(), ctx->d_total.as<unsigned long long>(), st)))
@@ -462,9 +463,10 @@ int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* camin, const gs
     if ((rc = launch_composite_bwd(is_sh ? PAY_SH : PAY_RGB, is_sh ? in->C : 1, extras, true, a, st))) return rc;
   }
   GSB_EV(ev, 1, st);
-  rc = launch_project_bwd_fused(N, in->mean, in->qvec, in->svec, g->mask, cam, ctx->ggeom.as<float4>(),
-                                  is_sh ? nullptr : ctx->gpay.as<float4>(), g->g_mean, g->g_qvec, g->g_svec,
-                                  g->g_alpha, is_sh ? nullptr : g->g_color, g->g_mean2d, g->accumulate, st);
+  rc = launch_project_bwd_fused(N, in->mean, in->qvec, in->svec, in->alpha, is_sh ? nullptr : in->color, in->act,
+                                g->mask, cam, ctx->ggeom.as<float4>(), is_sh ? nullptr : ctx->gpay.as<float4>(),
+                                g->g_mean, g->g_qvec, g->g_svec, g->g_alpha, is_sh ? nullptr : g->g_color,
+                                g->g_mean2d, g->accumulate, st);
   if (rc) return rc;
   GSB_EV(ev, 2, st);
   return GSB200_OK;

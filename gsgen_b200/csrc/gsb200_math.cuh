@@ -54,6 +54,21 @@ struct Camera {      // one view; plain floats so it can be passed by value to k
   int depth_detach;      // conf/renderer/base.yaml depth_detach (default True)
 };
 
+// ---- parameter activations of the fused front end ------------------------------------
+// The reference keeps svec / alpha / color as raw leaves and applies an activation in a property on every
+// access (gs/gaussian_splatting.py:113-123); every shipped config uses exp / sigmoid / sigmoid
+// (conf/renderer/base.yaml:14-16, utils/activations.py:36-45).  With `act` bits set the fused kernels take the
+// RAW leaves and return gradients w.r.t. them; the formulas are torch's (exp -> y, sigmoid -> y(1-y)).
+enum : int { kActSvecExp = 1, kActAlphaSigmoid = 2, kActColorSigmoid = 4 };
+GSB_HD float act_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+GSB_HD float act_svec(float raw, int act) { return (act & kActSvecExp) ? expf(raw) : raw; }
+GSB_HD float act_alpha(float raw, int act) { return (act & kActAlphaSigmoid) ? act_sigmoid(raw) : raw; }
+GSB_HD float act_color(float raw, int act) { return (act & kActColorSigmoid) ? act_sigmoid(raw) : raw; }
+// chain rule: gradient w.r.t. the raw leaf from the gradient w.r.t. the activated value y
+GSB_HD float act_svec_bwd(float g, float y, int act) { return (act & kActSvecExp) ? g * y : g; }
+GSB_HD float act_alpha_bwd(float g, float y, int act) { return (act & kActAlphaSigmoid) ? g * ((1.0f - y) * y) : g; }
+GSB_HD float act_color_bwd(float g, float y, int act) { return (act & kActColorSigmoid) ? g * ((1.0f - y) * y) : g; }
+
 // ---- A.2 -----------------------------------------------------------------------------------------
 GSB_HD bool sphere_in_frustum(const float m[3], float r, const float* fn, const float* fp) {
 #pragma unroll

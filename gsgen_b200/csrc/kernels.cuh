@@ -69,11 +69,11 @@ int launch_count_from_aabb(uint32_t N, const int32_t* tl, const int32_t* br, int
 int launch_pack_splats(uint32_t N, const float* mean2d, const float* cov2d, const float* alpha, const float* payload,
                        int pay_kind, Splat* splat, float4* pay, cudaStream_t st);
 int launch_preprocess(uint32_t N, const float* mean, const float* qvec, const float* svec, const float* alpha,
-                      const float* color, const Camera& cam, float* mean2d, float* cov2d, float* depthg,
+                      const float* color, int act, const Camera& cam, float* mean2d, float* cov2d, float* depthg,
                       uint8_t* mask, float* radii2d, Splat* splat, float4* pay, ushort4* rect, int32_t* count,
                       unsigned long long* total, cudaStream_t st);
 int launch_project_bwd_fused(uint32_t N, const float* mean, const float* qvec, const float* svec,
-                             const uint8_t* mask, const Camera& cam, const float4* ggeom, const float4* gpay,
+                             const float* alpha, const float* color, int act, const uint8_t* mask, const Camera& cam, const float4* ggeom, const float4* gpay,
                              float* g_mean, float* g_qvec, float* g_svec, float* g_alpha, float* g_color,
                              float* g_mean2d, int accumulate, cudaStream_t st);
 

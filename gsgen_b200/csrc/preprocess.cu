@@ -147,11 +147,13 @@ k_pack_splats(uint32_t N, const float* __restrict__ mean2d, const float* __restr
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int preprocess_one(
     uint32_t i, const float* __restrict__ mean, const float* __restrict__ qvec, const float* __restrict__ svec,
-    const float* __restrict__ alpha, const float* __restrict__ color, const Camera& cam, float* __restrict__ mean2d,
-    float* __restrict__ cov2d, float* __restrict__ depthg, uint8_t* __restrict__ mask, float* __restrict__ radii2d,
-    Splat* __restrict__ splat, float4* __restrict__ pay, ushort4* __restrict__ rect, int32_t* __restrict__ count) {
+    const float* __restrict__ alpha, const float* __restrict__ color, int act, const Camera& cam,
+    float* __restrict__ mean2d, float* __restrict__ cov2d, float* __restrict__ depthg, uint8_t* __restrict__ mask,
+    float* __restrict__ radii2d, Splat* __restrict__ splat, float4* __restrict__ pay, ushort4* __restrict__ rect,
+    int32_t* __restrict__ count) {
   float x[3] = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2]};
-  float s[3] = {svec[3 * i], svec[3 * i + 1], svec[3 * i + 2]};
+  // raw leaves -> activated values in registers; act == 0: the tensors are already activated
+  float s[3] = {act_svec(svec[3 * i], act), act_svec(svec[3 * i + 1], act), act_svec(svec[3 * i + 2], act)};
   bool keep = true;
   if (!cam.skip_frustum) {
     float r = fmaxf(fmaxf(s[0], s[1]), s[2]) * cam.frustum_radius;
@@ -174,7 +176,7 @@ __device__ __forceinline__ int preprocess_one(
   reinterpret_cast<float4*>(cov2d)[i] = make_float4(f.cov[0], f.cov[1], f.cov[2], f.cov[3]);
   depthg[i] = f.depth;
   if (radii2d) radii2d[i] = radius2d(f.cov);
-  Splat sp = make_splat(f.mean2d, f.cov, alpha[i]);
+  Splat sp = make_splat(f.mean2d, f.cov, act_alpha(alpha[i], act));
   int r[4];
   aabb_tiles(f.mean2d, f.cov[0], f.cov[3], cam.tile_radius, cam.fx, cam.fy, cam.cx, cam.cy, cam.W, cam.H, 16, r);
   int cnt = (r[2] - r[0] + 1) * (r[3] - r[1] + 1);
@@ -186,19 +188,21 @@ __device__ __forceinline__ int preprocess_one(
   float4* spp = reinterpret_cast<float4*>(splat + i);
   spp[0] = make_float4(sp.mx, sp.my, sp.p0, sp.p1);
   spp[1] = make_float4(sp.p2, sp.a, sp.hx, sp.hy);
-  if (color) pay[i] = make_float4(color[3 * i], color[3 * i + 1], color[3 * i + 2], f.depth);
+  if (color)
+    pay[i] = make_float4(act_color(color[3 * i], act), act_color(color[3 * i + 1], act),
+                         act_color(color[3 * i + 2], act), f.depth);
   return cnt;
 }
 
 __global__ void __launch_bounds__(kThreads)
 k_preprocess(uint32_t N, const float* __restrict__ mean, const float* __restrict__ qvec,
              const float* __restrict__ svec, const float* __restrict__ alpha, const float* __restrict__ color,
-             Camera cam, float* __restrict__ mean2d, float* __restrict__ cov2d, float* __restrict__ depthg,
+             int act, Camera cam, float* __restrict__ mean2d, float* __restrict__ cov2d, float* __restrict__ depthg,
              uint8_t* __restrict__ mask, float* __restrict__ radii2d, Splat* __restrict__ splat,
              float4* __restrict__ pay, ushort4* __restrict__ rect, int32_t* __restrict__ count,
              unsigned long long* __restrict__ total) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  block_add_total(i < N ? preprocess_one(i, mean, qvec, svec, alpha, color, cam, mean2d, cov2d, depthg, mask, radii2d,
+  block_add_total(i < N ? preprocess_one(i, mean, qvec, svec, alpha, color, act, cam, mean2d, cov2d, depthg, mask, radii2d,
                                          splat, pay, rect, count)
                         : 0,
                   total);
@@ -211,7 +215,8 @@ k_preprocess(uint32_t N, const float* __restrict__ mean, const float* __restrict
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 k_project_bwd_fused(uint32_t N, const float* __restrict__ mean, const float* __restrict__ qvec,
-                    const float* __restrict__ svec, const uint8_t* __restrict__ mask, Camera cam,
+                    const float* __restrict__ svec, const float* __restrict__ alpha,
+                    const float* __restrict__ color, int act, const uint8_t* __restrict__ mask, Camera cam,
                     const float4* __restrict__ ggeom, const float4* __restrict__ gpay, float* __restrict__ g_mean,
                     float* __restrict__ g_qvec, float* __restrict__ g_svec, float* __restrict__ g_alpha,
                     float* __restrict__ g_color, float* __restrict__ g_mean2d, int accumulate) {
@@ -225,7 +230,7 @@ k_project_bwd_fused(uint32_t N, const float* __restrict__ mean, const float* __r
     float x[3] = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2]};
     float4 q4 = reinterpret_cast<const float4*>(qvec)[i];
     float q[4] = {q4.x, q4.y, q4.z, q4.w};
-    float s[3] = {svec[3 * i], svec[3 * i + 1], svec[3 * i + 2]};
+    float s[3] = {act_svec(svec[3 * i], act), act_svec(svec[3 * i + 1], act), act_svec(svec[3 * i + 2], act)};
     Proj f;
     project_gaussian(x, q, s, cam, f);
     gm2[0] = g0.x; gm2[1] = g0.y;
@@ -233,6 +238,15 @@ k_project_bwd_fused(uint32_t N, const float* __restrict__ mean, const float* __r
     project_gaussian_bwd(s, cam, f, gm2, gc, g1.z, gx, gq, gs);
     ga = g1.y;
     if (gpay) { float4 p = gpay[i]; gcol[0] = p.x; gcol[1] = p.y; gcol[2] = p.z; }
+    if (act) {  // gradients w.r.t. the raw leaves (same expressions as torch's exp / sigmoid backward)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gs[k] = act_svec_bwd(gs[k], s[k], act);
+      if (act & kActAlphaSigmoid) ga = act_alpha_bwd(ga, act_sigmoid(alpha[i]), act);
+      if (gpay && (act & kActColorSigmoid)) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) gcol[k] = act_color_bwd(gcol[k], act_sigmoid(color[3 * i + k]), act);
+      }
+    }
   }
   if (g_mean2d) reinterpret_cast<float2*>(g_mean2d)[i] = make_float2(gm2[0], gm2[1]);
   if (accumulate) {  // += into the caller's running gradient (e.g. the flat all-reduce buffer); culled: no traffic
@@ -307,21 +321,21 @@ int launch_pack_splats(uint32_t N, const float* mean2d, const float* cov2d, cons
   return GSB200_OK;
 }
 int launch_preprocess(uint32_t N, const float* mean, const float* qvec, const float* svec, const float* alpha,
-                      const float* color, const Camera& cam, float* mean2d, float* cov2d, float* depthg,
+                      const float* color, int act, const Camera& cam, float* mean2d, float* cov2d, float* depthg,
                       uint8_t* mask, float* radii2d, Splat* splat, float4* pay, ushort4* rect, int32_t* count,
                       unsigned long long* total, cudaStream_t st) {
   if (N == 0) return GSB200_OK;
-  k_preprocess<<<grid1d(N), kThreads, 0, st>>>(N, mean, qvec, svec, alpha, color, cam, mean2d, cov2d, depthg, mask,
+  k_preprocess<<<grid1d(N), kThreads, 0, st>>>(N, mean, qvec, svec, alpha, color, act, cam, mean2d, cov2d, depthg, mask,
                                               radii2d, splat, pay, rect, count, total);
   GSB_LAUNCH_CHECK();
   return GSB200_OK;
 }
 int launch_project_bwd_fused(uint32_t N, const float* mean, const float* qvec, const float* svec,
-                             const uint8_t* mask, const Camera& cam, const float4* ggeom, const float4* gpay,
+                             const float* alpha, const float* color, int act, const uint8_t* mask, const Camera& cam, const float4* ggeom, const float4* gpay,
                              float* g_mean, float* g_qvec, float* g_svec, float* g_alpha, float* g_color,
                              float* g_mean2d, int accumulate, cudaStream_t st) {
   if (N == 0) return GSB200_OK;
-  k_project_bwd_fused<<<grid1d(N), kThreads, 0, st>>>(N, mean, qvec, svec, mask, cam, ggeom, gpay, g_mean, g_qvec,
+  k_project_bwd_fused<<<grid1d(N), kThreads, 0, st>>>(N, mean, qvec, svec, alpha, color, act, mask, cam, ggeom, gpay, g_mean, g_qvec,
                                                      g_svec, g_alpha, g_color, g_mean2d, accumulate);
   GSB_LAUNCH_CHECK();
   return GSB200_OK;

@@ -8,7 +8,11 @@ from ~60 torch kernels, 5 extension calls, 2 host syncs and 5 cudaMallocs per vi
     composite backward (all channels in one walk)  ->  fused projection backward
 
 Inputs are the POST-activation parameters, exactly what `render_one` hands to the rasterizer stage
-(`self.mean / qvec / svec / color / alpha`), so activations stay in torch as in the reference.
+(`self.mean / qvec / svec / color / alpha`), or -- with `raw_params=True` -- the RAW leaves
+(`svec_before_activation`, `alpha_before_activation`, `color_before_activation`, gs/gaussian_splatting.py:113-123)
+with the shipped activations exp / sigmoid / sigmoid (conf/renderer/base.yaml:14-16) evaluated inside the front-end
+kernel and their chain rule inside the projection backward: three fewer elementwise passes over the
+parameters in each direction, and the gradients land directly on the optimizer's leaves.
 """
 from __future__ import annotations
 
@@ -46,7 +50,7 @@ class _RenderView(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mean, qvec, svec, alpha, color, sh, bg, cam: Gsb200Camera, C, sh_c2w9, bg_rgb, rgb_only, slot,
-                aux, grad_sink):
+                aux, grad_sink, act=0):
         dev = mean.device
         N = mean.shape[0]
         H, W = cam.H, cam.W
@@ -56,6 +60,7 @@ class _RenderView(torch.autograd.Function):
         vin.N = N
         vin.mean, vin.qvec, vin.svec = fptr(mean, "mean"), fptr(qvec, "qvec"), fptr(svec, "svec")
         vin.alpha = fptr(alpha, "alpha")
+        vin.act = int(act)
         if is_sh:
             sh = sh.contiguous()
             if sh.shape[1:] != (3, C * C):
@@ -95,7 +100,7 @@ class _RenderView(torch.autograd.Function):
                                                     _lib.stream_ptr(dev)))
         ctx.save_for_backward(mean, qvec, svec, alpha, color, sh, bg, bg_rgb, rgb, depth, opacity, z2, T, mask)
         ctx.cam, ctx.C, ctx.sh_c2w9, ctx.slot, ctx.extras, ctx.aux = cam, C, sh_c2w9, slot, extras, aux
-        ctx.grad_sink = grad_sink
+        ctx.grad_sink, ctx.act = grad_sink, int(act)
         if aux is not None:
             aux.update(mask=mask, cov2d=cov2d, depth=depthg, radii2d=radii, N_with_dub=int(ndup.value))
         ctx.mark_non_differentiable(T)
@@ -113,6 +118,7 @@ class _RenderView(torch.autograd.Function):
         vin = Gsb200ViewIn()
         vin.N = N
         vin.mean, vin.qvec, vin.svec, vin.alpha = fptr(mean), fptr(qvec), fptr(svec), fptr(alpha)
+        vin.act = ctx.act
         if is_sh:
             vin.sh, vin.color, vin.C = fptr(sh), None, ctx.C
             vin.sh_c2w9 = (ctypes.c_float * 9)(*ctx.sh_c2w9)
@@ -153,19 +159,24 @@ class _RenderView(torch.autograd.Function):
         if ctx.aux is not None:  # what mean_2d.grad holds in the reference (retain_grad, :1247)
             ctx.aux["mean2d_grad"] = gm2
         if sink is not None:
-            return None, None, None, None, None, None, gbg, None, None, None, None, None, None, None, None
-        return gm, gq, gs, ga, gcol, gsh, gbg, None, None, None, None, None, None, None, None
+            return (None,) * 6 + (gbg,) + (None,) * 9
+        return (gm, gq, gs, ga, gcol, gsh, gbg) + (None,) * 9
 
 
 def render_view(mean, qvec, svec, alpha, c2w, camera_info, *, color=None, sh=None, C: int = 1, bg=None, bg_rgb=None,
                 rgb_only: bool = False, sh_c2w=None, frustum_radius=6.0, tile_radius=6.0, T_thresh=1e-4,
-                skip_frustum_culling=False, depth_detach=True, slot: int = 0, grad_sink=None):
+                skip_frustum_culling=False, depth_detach=True, slot: int = 0, grad_sink=None,
+                raw_params: bool = False):
     """One view through the fused path.  Returns the dict `render_one` returns
     ({"rgb","depth","opacity","z_var"} (+"T")) plus "aux" (mask, mean2d, cov2d, depth, radii2d, N_with_dub).
 
     grad_sink: optional dict name -> fp32 tensor (mean, qvec, svec, alpha, color | sh) shaped like the parameters;
                 the backward then ADDS the view's gradients into these tensors (e.g. views of one flat buffer that is
                 all-reduced once per step) and autograd receives None for them -- no zero-fill / add pass per view.
+
+    raw_params: svec / alpha / color are the raw leaves (`*_before_activation`); exp / sigmoid / sigmoid run inside the
+                kernels and the returned (or sunk) gradients are w.r.t. the raw leaves.  SH coefficients have no
+                activation in the reference (sh_renderer.py:38-43), so only svec / alpha are affected on the SH path.
 
     color given -> RGB path (render_with_T + 3x render_scalar semantics, per-pixel bg[H,W,3]);
     sh given    -> SH path  (render_sh / render_sh_bg semantics, constant bg_rgb[3]); `sh_c2w` is the tensor the
@@ -181,8 +192,12 @@ def render_view(mean, qvec, svec, alpha, c2w, camera_info, *, color=None, sh=Non
         src = c2w if sh_c2w is None else sh_c2w
         sh_c2w9 = src.detach().to("cpu", torch.float32).contiguous().view(-1)[:9].tolist()
     aux = {}
+    act = 0
+    if raw_params:
+        act = _lib.ACT_SVEC_EXP | _lib.ACT_ALPHA_SIGMOID | (_lib.ACT_COLOR_SIGMOID if sh is None else 0)
     rgb, depth, opacity, z2, T, mean2d = _RenderView.apply(mean, qvec, svec, alpha, color, sh, bg, cam, C, sh_c2w9,
-                                                           bg_rgb, rgb_only or sh is not None, slot, aux, grad_sink)
+                                                           bg_rgb, rgb_only or sh is not None, slot, aux, grad_sink,
+                                                           act)
     out = {"rgb": rgb, "T": T}
     if sh is None and not rgb_only:
         out.update(depth=depth, opacity=opacity, z_var=z2 - depth * depth)

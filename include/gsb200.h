@@ -171,18 +171,25 @@ typedef struct gsb200_camera {
   int32_t depth_detach;
 } gsb200_camera;
 
+#define GSB200_ACT_SVEC_EXP 1      /* svec  = exp(raw)      conf/renderer/base.yaml:14 */
+#define GSB200_ACT_ALPHA_SIGMOID 2 /* alpha = sigmoid(raw)  :15 */
+#define GSB200_ACT_COLOR_SIGMOID 4 /* color = sigmoid(raw)  :16 (RGB path; SH coefficients have no activation) */
 typedef struct gsb200_view_in {
   uint32_t N;
   const float* mean;   /* [N,3]                                                                   */
   const float* qvec;   /* [N,4] (w,x,y,z)                                                         */
-  const float* svec;   /* [N,3] post-activation                                                   */
-  const float* alpha;  /* [N]   post-activation                                                   */
-  const float* color;  /* [N,3] post-activation RGB, or NULL when sh != NULL                      */
+  const float* svec;   /* [N,3] post-activation (raw when act & GSB200_ACT_SVEC_EXP)               */
+  const float* alpha;  /* [N]   post-activation (raw when act & GSB200_ACT_ALPHA_SIGMOID)          */
+  const float* color;  /* [N,3] post-activation RGB (raw when act & ..COLOR_SIGMOID); NULL with sh  */
   const float* sh;     /* [N,3,C*C] or NULL                                                       */
   int32_t C;           /* SH template parameter (degree+1), 1..4                                  */
   float sh_c2w9[9];    /* the nine floats the SH kernels read as rotation rows (A.7)              */
   const float* bg;     /* [H,W,3] per-pixel background (RGB path) or NULL                         */
   const float* bg_rgb; /* [3] constant background (SH path) or NULL                               */
+  int32_t act;         /* GSB200_ACT_* bits: the tensors above are the RAW leaves                     */
+                       /* (svec_before_activation ... gs/gaussian_splatting.py:113-123) and the        */
+                       /* activation runs inside the front-end kernel; render_backward then returns    */
+                       /* gradients w.r.t. the raw leaves.  0 = post-activation tensors (as _gs takes) */
 } gsb200_view_in;
 
 typedef struct gsb200_view_out {

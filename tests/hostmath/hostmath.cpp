@@ -87,4 +87,30 @@ void hm_sh_basis(int C, const float* pos2, const float* c9, float* out16) {
     default: sh_basis<4>(d[0], d[1], d[2], out16); break;
   }
 }
+
+// Per-Gaussian slice of the fused front end with in-kernel activations, as k_preprocess /
+// k_project_bwd_fused evaluate it: raw leaves -> activated values -> projection, and back to raw-leaf gradients.
+void hm_front_end_raw(int N, int act, const float* mean, const float* qvec, const float* svec_raw,
+                      const float* alpha_raw, const float* color_raw, const float* c2w12, float* mean2d, float* cov2d,
+                      float* alpha_act, float* color_act, const float* g_m2, const float* g_cov,
+                      const float* g_alpha_act, const float* g_color_act, float* g_mean, float* g_qvec,
+                      float* g_svec_raw, float* g_alpha_raw, float* g_color_raw) {
+  Camera cam = make_cam(c2w12, 1);
+  for (int i = 0; i < N; ++i) {
+    float s[3];
+    for (int k = 0; k < 3; ++k) s[k] = act_svec(svec_raw[3 * i + k], act);
+    Proj f;
+    project_gaussian(mean + 3 * i, qvec + 4 * i, s, cam, f);
+    mean2d[2 * i] = f.mean2d[0]; mean2d[2 * i + 1] = f.mean2d[1];
+    for (int k = 0; k < 4; ++k) cov2d[4 * i + k] = f.cov[k];
+    alpha_act[i] = act_alpha(alpha_raw[i], act);
+    for (int k = 0; k < 3; ++k) color_act[3 * i + k] = act_color(color_raw[3 * i + k], act);
+    float gs[3];
+    project_gaussian_bwd(s, cam, f, g_m2 + 2 * i, g_cov + 4 * i, 0.f, g_mean + 3 * i, g_qvec + 4 * i, gs);
+    for (int k = 0; k < 3; ++k) g_svec_raw[3 * i + k] = act_svec_bwd(gs[k], s[k], act);
+    g_alpha_raw[i] = act_alpha_bwd(g_alpha_act[i], alpha_act[i], act);
+    for (int k = 0; k < 3; ++k)
+      g_color_raw[3 * i + k] = act_color_bwd(g_color_act[3 * i + k], color_act[3 * i + k], act);
+  }
+}
 }

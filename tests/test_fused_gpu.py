@@ -201,3 +201,50 @@ def test_grad_sink_accumulates():
         assert m2.grad is None and sh2.grad is None
     for k in ref:
         assert_grad_close(sink[k], 2 * ref[k], 1e-5, f"sink {k}")
+
+
+@pytest.mark.parametrize("path", ["rgb", "sh"])
+def test_raw_params_equal_torch_activations(path):
+    """`raw_params=True` takes svec/alpha/color *_before_activation and must equal
+    render_view(exp(raw), sigmoid(raw), sigmoid(raw)) with the activations and their backward run by torch
+    (gs/gaussian_splatting.py:113-123) -- images to 1e-5, raw-leaf gradients to 1e-3 relative."""
+    from gsgen_b200.rasterizer import render_view
+
+    sc = make_scene("c3", N=6000, reso=160).to(DEV)
+    sc.svec = (sc.svec * 3.0).contiguous()
+    cam, c2w = sc.cams[0], sc.c2ws[0].cpu()
+    g = torch.Generator().manual_seed(9)
+    w = torch.randn(cam.h, cam.w, 3, generator=g).to(DEV)
+    raw0 = dict(svec=torch.log(sc.svec), alpha=torch.logit(sc.alpha), color=torch.logit(sc.color.clamp(0.02, 0.98)))
+
+    def run(fused):
+        mean, qvec = sc.mean.clone().requires_grad_(), sc.qvec.clone().requires_grad_()
+        raw = {k: v.clone().requires_grad_() for k, v in raw0.items()}
+        sh = sc.sh.clone().requires_grad_()
+        if fused:
+            s, a, c = raw["svec"], raw["alpha"], raw["color"]
+        else:
+            s, a, c = torch.exp(raw["svec"]), torch.sigmoid(raw["alpha"]), torch.sigmoid(raw["color"])
+        kw = dict(sh=sh, C=4) if path == "sh" else dict(color=c, rgb_only=False)
+        out = render_view(mean, qvec, s, a, c2w, cam, raw_params=fused, **kw)
+        loss = (out["rgb"] * w).sum()
+        if path == "rgb":
+            loss = loss + (out["depth"] * w[..., :1]).sum() + (out["opacity"] * w[..., 1:2]).sum()
+        loss.backward()
+        grads = dict(mean=mean.grad, qvec=qvec.grad, svec_raw=raw["svec"].grad, alpha_raw=raw["alpha"].grad)
+        if path == "rgb":
+            grads["color_raw"] = raw["color"].grad
+        else:
+            grads["sh"] = sh.grad
+        return out, grads
+
+    o_ref, g_ref = run(False)
+    o_fus, g_fus = run(True)
+    # expf / the sigmoid quotient are the same device functions torch calls, so the two runs are expected to agree to
+    # the last bit; the bounds leave room for a 1-ulp libdevice difference flipping a frustum / 1/255 / T threshold
+    assert int((o_ref["aux"]["mask"] != o_fus["aux"]["mask"]).sum()) <= 2
+    assert abs(o_ref["aux"]["N_with_dub"] - o_fus["aux"]["N_with_dub"]) <= 8
+    diff = (o_ref["rgb"] - o_fus["rgb"]).abs()
+    assert float((diff > 1e-5).float().mean()) <= 1e-3 and float(diff.max()) <= 5e-3, float(diff.max())
+    for k in g_ref:
+        assert_grad_close(g_fus[k], g_ref[k], 1e-3, f"raw_params {path} {k}")

@@ -149,3 +149,38 @@ def test_sh_basis_matches_oracle(hostmath, oracle_mod, C):
         oracle_mod.lib().orc_pixel_dir(fp(pos3), fp(c9), fp(d))
         oracle_mod.lib().orc_sh_basis(fp(d), fp(ref), C)
         assert torch.allclose(ours[: C * C], ref[: C * C], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("act", [0, 7, 1, 6])
+def test_in_kernel_activations_match_torch_chain_rule(hostmath, oracle_mod, act):
+    """raw leaves in, raw-leaf gradients out.  torch applies exp / sigmoid / sigmoid in the
+    `svec` / `alpha` / `color` properties (gs/gaussian_splatting.py:113-123); the fused front end evaluates them in
+    registers and the projection backward applies their chain rule."""
+    sc, cam, c2w = _scene(N=2500)
+    g = torch.Generator().manual_seed(11)
+    N = sc.N
+    svec_raw = (torch.log(sc.svec) if act & 1 else sc.svec).clone().requires_grad_()
+    alpha_raw = (torch.logit(sc.alpha.view(-1)) if act & 2 else sc.alpha.view(-1)).clone().requires_grad_()
+    color_raw = (torch.logit(sc.color.clamp(0.02, 0.98)) if act & 4 else sc.color).clone().requires_grad_()
+    mean = sc.mean.clone().requires_grad_()
+    q = sc.qvec.clone().requires_grad_()
+    s = torch.exp(svec_raw) if act & 1 else svec_raw
+    a = torch.sigmoid(alpha_raw) if act & 2 else alpha_raw
+    c = torch.sigmoid(color_raw) if act & 4 else color_raw
+    m2, cov, _, _ = oracle_mod.project_gaussians(mean, q, s, c2w, True)
+    gm2, gcov = torch.randn(N, 2, generator=g), torch.randn(N, 2, 2, generator=g)
+    ga, gc = torch.randn(N, generator=g), torch.randn(N, 3, generator=g)
+    ((m2 * gm2).sum() + (cov * gcov).sum() + (a * ga).sum() + (c * gc).sum()).backward()
+    o_m2, o_cov, o_a, o_c = torch.empty(N, 2), torch.empty(N, 4), torch.empty(N), torch.empty(N, 3)
+    gx, gq, gs, gar, gcr = torch.empty(N, 3), torch.empty(N, 4), torch.empty(N, 3), torch.empty(N), torch.empty(N, 3)
+    hostmath.hm_front_end_raw(N, act, fp(sc.mean), fp(sc.qvec), fp(svec_raw.detach()), fp(alpha_raw.detach()),
+                              fp(color_raw.detach().contiguous()), fp(c2w.contiguous()), fp(o_m2), fp(o_cov), fp(o_a),
+                              fp(o_c), fp(gm2), fp(gcov.reshape(N, 4).contiguous()), fp(ga), fp(gc), fp(gx), fp(gq),
+                              fp(gs), fp(gar), fp(gcr))
+    assert torch.allclose(o_a, a.detach(), rtol=1e-6, atol=1e-7)
+    assert torch.allclose(o_c, c.detach(), rtol=1e-6, atol=1e-7)
+    assert torch.allclose(o_m2, m2.detach(), rtol=2e-5, atol=1e-6)
+    for ours, ref, nm in ((gx, mean.grad, "mean"), (gq, q.grad, "qvec"), (gs, svec_raw.grad, "svec_raw"),
+                          (gar, alpha_raw.grad, "alpha_raw"), (gcr, color_raw.grad, "color_raw")):
+        rel = (ours - ref).norm() / ref.norm()
+        assert float(rel) < 1e-4, (nm, float(rel))
