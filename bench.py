@@ -576,6 +576,8 @@ def run_ours(args):
         mode, e2e_runs, pipe_err = "serial", serial_runs, None
         ok = torch.ones(1, device=dev)
         try:
+            if world > 1:  # validated on one GPU only in round 1; multi-rank keeps the single-stream schedule
+                raise RuntimeError("side-stream schedule not enabled for world_size > 1")
             pipe_runs = e2e_measure(e2e_step_pipelined)
             torch.cuda.synchronize()
             # the image that reached the host must be the image the device holds
