@@ -50,6 +50,10 @@ class Gsb200ViewIn(ctypes.Structure):
     ]
 
 
+class Gsb200AdamField(ctypes.Structure):
+    _fields_ = [("begin", ctypes.c_uint64), ("count", ctypes.c_uint64), ("lr", ctypes.c_double)]
+
+
 ACT_SVEC_EXP, ACT_ALPHA_SIGMOID, ACT_COLOR_SIGMOID = 1, 2, 4  # GSB200_ACT_* (include/gsb200.h)
 
 
@@ -88,7 +92,7 @@ EXPORTS = [
     "gsb200_tile_based_vol_rendering_sh", "gsb200_tile_based_vol_rendering_backward_sh",
     "gsb200_project_gaussians_forward", "gsb200_project_gaussians_backward", "gsb200_tile_culling_aabb_count",
     "gsb200_render_forward", "gsb200_render_backward", "gsb200_view_stats",
-    "gsb200_ctx_set_profiling", "gsb200_ctx_get_profile",
+    "gsb200_ctx_set_profiling", "gsb200_ctx_get_profile", "gsb200_adam_step",
 ]
 
 

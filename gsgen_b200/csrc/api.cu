@@ -1,5 +1,6 @@
 // api.cu -- the extern "C" surface of libgsb200.so (include/gsb200.h).  Argument validation mirrors the
 // reference's TORCH_CHECK contracts (gs/src/include/common.h:29-54) but reports through return codes.
+#include <math.h>
 #include <stdarg.h>
 
 #include "kernels.cuh"
@@ -470,6 +471,47 @@ int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* camin, const gs
   if (rc) return rc;
   GSB_EV(ev, 2, st);
   return GSB200_OK;
+}
+
+// ---- Part 4 -------------------------------------------------------------------------------------------
+int gsb200_adam_step(gsb200_ctx* ctx, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                     uint64_t total, const gsb200_adam_field* fields, int32_t n_fields, double beta1, double beta2,
+                     double eps, int64_t step, float grad_scale, gsb200_stream stream) {
+  int rc;
+  if ((rc = set_device(ctx))) return rc;
+  if (total == 0) return GSB200_OK;
+  GSB_CHECK(param && grad && exp_avg && exp_avg_sq && fields, GSB200_ERR_INVALID, "adam_step: null argument");
+  GSB_CHECK(n_fields >= 1 && n_fields <= 8, GSB200_ERR_INVALID, "adam_step: n_fields=%d not in 1..8", n_fields);
+  GSB_CHECK(step >= 1, GSB200_ERR_INVALID, "adam_step: step counts from 1 (torch state['step']), got %lld",
+            (long long)step);
+  GSB_CHECK(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
+              reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0,
+            GSB200_ERR_INVALID, "adam_step: buffers must be 16-byte aligned");
+  AdamFields F{};
+  F.n = n_fields;
+  uint64_t at = 0;
+  // bias corrections in double, like the Python floats torch computes them in (torch/optim/adam.py)
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  for (int f = 0; f < n_fields; ++f) {
+    GSB_CHECK(fields[f].begin == at, GSB200_ERR_INVALID,
+              "adam_step: fields must tile the buffer in order (field %d begins at %llu, expected %llu)", f,
+              (unsigned long long)fields[f].begin, (unsigned long long)at);
+    F.begin[f] = at;
+    F.step_size[f] = (float)(fields[f].lr / bc1);
+    at += fields[f].count;
+  }
+  GSB_CHECK(at == total, GSB200_ERR_INVALID, "adam_step: fields cover %llu of %llu elements",
+            (unsigned long long)at, (unsigned long long)total);
+  for (int f = n_fields; f <= 8; ++f) F.begin[f] = total;
+  AdamScalars K;
+  K.beta2 = (float)beta2;
+  K.one_minus_beta1 = (float)(1.0 - beta1);
+  K.one_minus_beta2 = (float)(1.0 - beta2);
+  K.eps = (float)eps;
+  K.bc2_sqrt = (float)sqrt(bc2);
+  K.grad_scale = grad_scale;
+  return launch_adam_flat(param, grad, exp_avg, exp_avg_sq, total, F, K, (cudaStream_t)stream);
 }
 
 int gsb200_ctx_set_profiling(gsb200_ctx* ctx, int enable) {

@@ -69,6 +69,22 @@ GSB_HD float act_svec_bwd(float g, float y, int act) { return (act & kActSvecExp
 GSB_HD float act_alpha_bwd(float g, float y, int act) { return (act & kActAlphaSigmoid) ? g * ((1.0f - y) * y) : g; }
 GSB_HD float act_color_bwd(float g, float y, int act) { return (act & kActColorSigmoid) ? g * ((1.0f - y) * y) : g; }
 
+// ---- Adam on the flat parameter buffer ---------------------------------------------------
+// torch.optim.Adam(amsgrad=False, weight_decay=0) as the reference configures it (conf/base.yaml:8-11: eps 1e-15;
+// gs/gaussian_splatting.py:398-419: one param group per field, lr from the field's scheduler).  Same expression
+// order as torch's kernels: lerp, mul+addcmul, sqrt / bias_correction2_sqrt + eps, addcdiv.
+struct AdamScalars {
+  float beta2, one_minus_beta1, one_minus_beta2, eps, bc2_sqrt, grad_scale;
+};
+GSB_HD void adam_update(float& p, float g, float& m, float& v, float step_size, const AdamScalars& k) {
+  g *= k.grad_scale;
+  m = m + k.one_minus_beta1 * (g - m);
+  v = v * k.beta2;
+  v = v + (k.one_minus_beta2 * g) * g;
+  const float denom = sqrtf(v) / k.bc2_sqrt + k.eps;
+  p = p - step_size * (m / denom);
+}
+
 // ---- A.2 -----------------------------------------------------------------------------------------
 GSB_HD bool sphere_in_frustum(const float m[3], float r, const float* fn, const float* fp) {
 #pragma unroll

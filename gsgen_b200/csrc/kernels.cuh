@@ -77,6 +77,15 @@ int launch_project_bwd_fused(uint32_t N, const float* mean, const float* qvec, c
                              float* g_mean, float* g_qvec, float* g_svec, float* g_alpha, float* g_color,
                              float* g_mean2d, int accumulate, cudaStream_t st);
 
+// optimizer.cu
+struct AdamFields {
+  int n;
+  unsigned long long begin[9];  // field f covers [begin[f], begin[f+1]); begin[n] = total
+  float step_size[8];           // lr_f / (1 - beta1^step)
+};
+int launch_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, unsigned long long total,
+                     const AdamFields& fields, const AdamScalars& k, cudaStream_t st);
+
 // binning.cu
 int begin_total(gsb200_ctx* ctx, cudaStream_t st);    // zero the device-side duplicate counter
 int request_total(gsb200_ctx* ctx, cudaStream_t st);  // async D2H copy + event

@@ -250,6 +250,27 @@ int gsb200_ctx_get_profile(gsb200_ctx* ctx, float* h_ms /*[6]*/, int64_t* h_coun
  * h_out[1]=number of Gaussians passing the frustum test, h_out[2]=max tile list length */
 int gsb200_view_stats(gsb200_ctx* ctx, int64_t* h_out, gsb200_stream stream);
 
+/* ================================================================================================
+ * Part 4 -- the step after the gradient all-reduce: torch.optim.Adam as the reference
+ * configures it (conf/base.yaml:8-11, eps 1e-15; gs/gaussian_splatting.py:398-419, one param group and one
+ * learning-rate schedule per field) applied to the FLAT fp32 buffers the multi-GPU path already owns
+ * ([mean | qvec | svec | alpha | color or sh], gsgen_b200/parallel.py) in one streaming pass:
+ * 16 B read + 12 B written per parameter.  `fields` tile [0, total) in ascending order; `lr` is the value the
+ * field's scheduler returns for this step (update_lr, gaussian_splatting.py:451-454); `step` counts from 1 as
+ * torch's state["step"]; gradients are multiplied by `grad_scale` first (1 = torch semantics; 1/global_batch
+ * turns the SUM all-reduce into a mean).  lr / betas / eps are doubles because torch holds them as Python floats and
+ * forms 1-beta and lr/(1-beta^step) in double before rounding to fp32.
+ * ============================================================================================== */
+typedef struct gsb200_adam_field {
+  uint64_t begin;  /* first element of the field in the flat buffers */
+  uint64_t count;  /* elements                                       */
+  double lr;       /* Python float of the param group, as torch receives it */
+} gsb200_adam_field;
+
+int gsb200_adam_step(gsb200_ctx* ctx, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                     uint64_t total, const gsb200_adam_field* fields, int32_t n_fields /* <= 8 */, double beta1,
+                     double beta2, double eps, int64_t step, float grad_scale, gsb200_stream stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

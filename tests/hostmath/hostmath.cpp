@@ -113,4 +113,21 @@ void hm_front_end_raw(int N, int act, const float* mean, const float* qvec, cons
       g_color_raw[3 * i + k] = act_color_bwd(g_color_act[3 * i + k], color_act[3 * i + k], act);
   }
 }
+
+// One Adam update of n elements with the expression order of k_adam_flat; the scalars are derived
+// exactly as gsb200_adam_step derives them.
+void hm_adam(long long n, float* p, const float* g, float* m, float* v, double lr, double beta1, double beta2,
+             double eps, long long step, float grad_scale) {
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  AdamScalars K;
+  K.beta2 = (float)beta2;
+  K.one_minus_beta1 = (float)(1.0 - beta1);
+  K.one_minus_beta2 = (float)(1.0 - beta2);
+  K.eps = (float)eps;
+  K.bc2_sqrt = (float)sqrt(bc2);
+  K.grad_scale = grad_scale;
+  const float step_size = (float)(lr / bc1);
+  for (long long i = 0; i < n; ++i) adam_update(p[i], g[i], m[i], v[i], step_size, K);
+}
 }
