@@ -76,23 +76,32 @@ class FlatAdam:
     """
 
     def __init__(self, flat_param: torch.Tensor, flat_grad: torch.Tensor, layout, lr: Dict[str, LrSpec],
-                 max_steps: int = 15000, betas=(0.9, 0.999), eps: float = 1e-15):
-        if flat_param.shape != flat_grad.shape or flat_param.dim() != 1:
-            raise RuntimeError("flat_param and flat_grad must be 1-D tensors of the same length")
-        if len(layout) > 8:
-            raise RuntimeError("at most 8 fields")
-        self.flat_param, self.flat_grad = flat_param, flat_grad
-        self.layout = list(layout)
+                 max_steps: int = 15000, betas=(0.9, 0.999), eps: float = 1e-15, state=None):
         self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
         self.schedulers = {}
-        for name, _, _, _ in self.layout:
+        for name, _, _, _ in layout:
             if name not in lr:
                 raise RuntimeError(f"no learning rate for field '{name}'")
             self.schedulers[name] = make_scheduler(lr[name], max_steps)
-        # state (torch: state[p]["exp_avg"], ["exp_avg_sq"], ["step"])
-        self.exp_avg = torch.zeros_like(flat_param)
-        self.exp_avg_sq = torch.zeros_like(flat_param)
-        self.n_steps = 0
+        self.n_steps = 0  # torch: state[p]["step"], shared by all rows (the reference keeps it across densify / prune)
+        # moments (torch: state[p]["exp_avg"], ["exp_avg_sq"]); `state` = buffers owned by a GaussianStore
+        exp_avg, exp_avg_sq = state if state is not None else (torch.zeros_like(flat_param),
+                                                                torch.zeros_like(flat_param))
+        self.rebind(flat_param, flat_grad, layout, exp_avg, exp_avg_sq)
+
+    def rebind(self, flat_param, flat_grad, layout, exp_avg, exp_avg_sq):
+        """Point the optimizer at (re-allocated or re-laid-out) buffers; the step counter and schedules are kept.
+        Called by `GaussianStore` after densify / prune, which is all the optimizer surgery the reference's
+        `densify_on_optimizer` / `prune_optimizer` (gs/gaussian_splatting.py:421-449, :481-522) amount to here."""
+        if flat_param.dim() != 1 or any(t.shape != flat_param.shape for t in (flat_grad, exp_avg, exp_avg_sq)):
+            raise RuntimeError("flat_param, flat_grad and the moment buffers must be 1-D tensors of the same length")
+        if len(layout) > 8:
+            raise RuntimeError("at most 8 fields")
+        self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq = flat_param, flat_grad, exp_avg, exp_avg_sq
+        self.layout = list(layout)
+        for name, _, _, _ in self.layout:
+            if name not in self.schedulers:
+                raise RuntimeError(f"no learning rate for field '{name}'")
         self._fields = (Gsb200AdamField * len(self.layout))()
         for i, (_, _, off, n) in enumerate(self.layout):
             self._fields[i].begin, self._fields[i].count = off, n

@@ -1,0 +1,275 @@
+"""Persistent capacity arena for the Gaussians and their Adam state, with densify / prune as row operations on
+it.
+
+Reference behaviour restated (gs/gaussian_splatting.py): every densify / prune step re-creates each parameter as a
+new `nn.Parameter` (`torch.cat` / boolean-mask indexing), deletes and re-inserts the Adam state of its param group
+with the same surgery (`densify_on_optimizer` :481-522, `prune_optimizer` :421-449), and re-slices the densification
+statistics (`prune_by_mask` :528-549).  That is ~10 allocations and copies of every tensor per operation plus a
+rebuild of the optimizer's state dict.
+
+Here the parameters, their gradients and both Adam moments live in four flat fp32 buffers with the SAME field-major
+layout (`field_layout(capacity, C)`): field f occupies `capacity * width_f` floats and its first `N` rows are live.
+  * append (clone / split children): rows are written behind row N of every field -- nothing else moves; the
+    Adam moments of new rows are zero (the reference concatenates `zeros_like`), the shared step counter is kept
+    (the reference skips 0-dim state entries).
+  * prune: a stable compaction of the live rows of every field, in place, by one gather per field and buffer.
+  * growth: only when `N + k > capacity` (capacity grows geometrically), one copy of the live rows.
+The live gradient rows are what the multi-GPU step all-reduces; `gsgen_b200.optim.FlatAdam` steps the whole arena in
+one kernel (dead rows carry zero gradients and zero moments, so they do not move).
+
+Row movers are torch indexing ops on the device the buffers live on (they are HBM-bound gathers; a hand-written mover
+is a later step) -- this file is host logic like `parallel.py` and is exercised on CPU tensors by the test-suite.
+Selection rules follow the reference bit for bit, including two quirks that a drop-in must keep:
+  * `densify_by_clone` compares `torch.norm(grads, dim=-1)` of the 1-D per-Gaussian statistic, i.e. ONE number for the
+    whole scene, with the threshold (:616-618);
+  * `prune_by_mask` re-slices the statistics with the post-densify mask and falls back to zeros when their length no
+    longer matches (:533-549).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from .parallel import field_layout
+
+
+def quat_to_rotmat(q: torch.Tensor) -> torch.Tensor:
+    """kornia 0.6.0 `quaternion_to_rotation_matrix(q, WXYZ)` (utils/transforms.py:53-54): normalise (eps 1e-12), then
+    the unit-quaternion matrix.  Same restatement as the kernels' `quat_to_rotmat` (csrc/gsb200_math.cuh)."""
+    q = torch.nn.functional.normalize(q, p=2.0, dim=-1, eps=1e-12)
+    w, x, y, z = q.unbind(-1)
+    tx, ty, tz = 2.0 * x, 2.0 * y, 2.0 * z
+    twx, twy, twz = tx * w, ty * w, tz * w
+    txx, txy, txz = tx * x, ty * x, tz * x
+    tyy, tyz, tzz = ty * y, tz * y, tz * z
+    one = torch.ones_like(w)
+    return torch.stack([one - (tyy + tzz), txy - twz, txz + twy,
+                        txy + twz, one - (txx + tzz), tyz - twx,
+                        txz - twy, tyz + twx, one - (txx + tyy)], dim=-1).view(*q.shape[:-1], 3, 3)
+
+
+class GaussianStore:
+    """Raw leaves (`mean`, `qvec`, `svec` = log scale, `alpha` = logit opacity, `color` = logit RGB | `sh`) in a
+    capacity arena.  `params[name]` are views of the live rows (autograd leaves whose `.grad` is a view of the flat
+    gradient buffer), re-created after every operation that changes N -- as the reference re-creates its Parameters.
+    """
+
+    def __init__(self, params: Dict[str, torch.Tensor], C: Optional[int], device=None, capacity: Optional[int] = None,
+                 growth: float = 1.5, group=None):
+        self.C, self.group, self.growth = C, group, float(growth)
+        self.device = torch.device(device) if device is not None else params["mean"].device
+        self.N = int(params["mean"].shape[0])
+        self.cap = max(int(capacity or 0), self.N, 1)
+        self.optimizer = None
+        self._alloc(self.cap)
+        for name, shape, off, n in field_layout(self.N, C):
+            self._rows(self.flat_param, name, self.N).copy_(params[name].detach().to(self.device, torch.float32)
+                                                           .reshape(self.N, -1))
+        self.reset_densify_info()
+        self._make_leaves()
+
+    # ---- arena ---------------------------------------------------------------------------------------
+    def _alloc(self, cap: int):
+        self.cap = cap
+        self.layout = field_layout(cap, self.C)
+        total = self.layout[-1][2] + self.layout[-1][3]
+        mk = lambda: torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq = mk(), mk(), mk(), mk()
+        self._field = {name: (shape, off) for name, shape, off, _ in self.layout}
+
+    def _buffers(self):
+        return (self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq)
+
+    def _rows(self, buf: torch.Tensor, name: str, n: int, start: int = 0) -> torch.Tensor:
+        """rows [start, start+n) of field `name` as a 2-D [n, width] view of `buf`"""
+        shape, off = self._field[name]
+        w = 1
+        for s in shape[1:]:
+            w *= s
+        return buf[off + start * w: off + (start + n) * w].view(n, w)
+
+    def _make_leaves(self):
+        self.params: Dict[str, torch.Tensor] = {}
+        self.grad_views: Dict[str, torch.Tensor] = {}
+        for name, (shape, _) in self._field.items():
+            live = (self.N,) + tuple(shape[1:])
+            p = self._rows(self.flat_param, name, self.N).view(live)
+            p.requires_grad_(True)
+            self.params[name] = p
+            self.grad_views[name] = self._rows(self.flat_grad, name, self.N).view(live)
+        if self.optimizer is not None:
+            self.optimizer.rebind(self.flat_param, self.flat_grad, self.layout, self.exp_avg, self.exp_avg_sq)
+
+    def _grow(self, need: int):
+        old = (self._buffers(), dict(self._field), self.N)
+        new_cap = max(need, int(self.cap * self.growth) + 1)
+        old_bufs, old_field, n = old
+        old_rows = {name: [self._rows(b, name, n) for b in old_bufs] for name in old_field}
+        self._alloc(new_cap)
+        for name, rows in old_rows.items():
+            for dst, src in zip(self._buffers(), rows):
+                self._rows(dst, name, n).copy_(src)
+
+    # ---- activated values (`self.svec` / `self.alpha` of the reference, :113-119) ---------------------------
+    @property
+    def svec_act(self) -> torch.Tensor:
+        return torch.exp(self.params["svec"].detach())
+
+    @property
+    def alpha_act(self) -> torch.Tensor:
+        return torch.sigmoid(self.params["alpha"].detach())
+
+    def make_optimizer(self, lr, max_steps: int = 15000, betas=(0.9, 0.999), eps: float = 1e-15):
+        """`set_optimizer` (:398-419): Adam over the whole arena, moments owned by the store so that they follow
+        their rows through densify / prune."""
+        from .optim import FlatAdam
+
+        self.optimizer = FlatAdam(self.flat_param, self.flat_grad, self.layout, lr, max_steps, betas, eps,
+                                  state=(self.exp_avg, self.exp_avg_sq))
+        return self.optimizer
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+        for name, p in self.params.items():
+            p.grad = self.grad_views[name]
+
+    def grad_bytes(self) -> int:
+        return sum(v.numel() for v in self.grad_views.values()) * 4
+
+    def all_reduce(self):
+        """SUM over ranks of the live gradient rows (one flat collective when the arena is full, else one per
+        field -- dead capacity is not sent)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return
+        if self.N == self.cap:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            for name in self._field:
+                dist.all_reduce(self._rows(self.flat_grad, name, self.N), op=dist.ReduceOp.SUM, group=self.group)
+
+    # ---- densification statistics (gs/gaussian_splatting.py:464-479) ---------------------------------------
+    def reset_densify_info(self):
+        z = lambda: torch.zeros(self.N, dtype=torch.float32, device=self.device)
+        self.mean_2d_grad_accum, self.cnt, self.max_radii2d = z(), z(), z()
+
+    def update_densify_info(self, mask: torch.Tensor, mean2d_grad: torch.Tensor, radii2d: Optional[torch.Tensor] = None):
+        """One rendered view: `mask` [N] bool, `mean2d_grad` [N,2] (aux["mean2d_grad"] of render_view, zero rows for
+        culled Gaussians), optional `radii2d` [N] (aux["radii2d"]).  :464-469 and :1240-1245."""
+        self.mean_2d_grad_accum[mask] += mean2d_grad[mask].norm(dim=-1)
+        self.cnt[mask] += 1
+        if radii2d is not None:
+            self.max_radii2d[mask] = torch.max(self.max_radii2d[mask], radii2d[mask])
+
+    # ---- row operations ----------------------------------------------------------------------------------
+    def append(self, new_params: Dict[str, torch.Tensor]) -> int:
+        """`densify_with_new_params` (:481-526): new rows behind the live ones, zero Adam moments."""
+        k = int(new_params["mean"].shape[0])
+        if k == 0:
+            return 0
+        if self.N + k > self.cap:
+            self._grow(self.N + k)
+        for name in self._field:
+            self._rows(self.flat_param, name, k, self.N).copy_(new_params[name].detach().reshape(k, -1))
+            for buf in (self.flat_grad, self.exp_avg, self.exp_avg_sq):
+                self._rows(buf, name, k, self.N).zero_()
+        self.N += k
+        self._make_leaves()
+        return k
+
+    def prune_by_mask(self, mask: torch.Tensor) -> int:
+        """`prune_by_mask` (:528-549): rows with mask=True are removed, order of the others kept; Adam moments follow
+        their rows (`prune_optimizer` :421-449)."""
+        if mask.shape[0] != self.N:
+            raise RuntimeError(f"prune mask has {mask.shape[0]} rows, the store {self.N}")
+        keep = (~mask.to(self.device)).nonzero(as_tuple=True)[0]
+        n_keep = int(keep.shape[0])
+        if n_keep < self.N:
+            for buf in self._buffers():
+                for name in self._field:
+                    live = self._rows(buf, name, self.N)
+                    gathered = live.index_select(0, keep)  # temporary: source and destination overlap
+                    live[:n_keep].copy_(gathered)
+                    live[n_keep:].zero_()  # dead rows: zero gradient / moments, so FlatAdam leaves them alone
+        n_pruned = self.N - n_keep
+        # statistics: re-sliced when their length matches the mask, zeros otherwise (the IndexError branches)
+        for attr in ("max_radii2d", "mean_2d_grad_accum", "cnt"):
+            t = getattr(self, attr)
+            setattr(self, attr, t.index_select(0, keep) if t.shape[0] == self.N else
+                    torch.zeros(n_keep, dtype=torch.float32, device=self.device))
+        self.N = n_keep
+        self._make_leaves()
+        return n_pruned
+
+    # ---- selection rules ---------------------------------------------------------------------------------
+    def densify_by_clone(self, grads: torch.Tensor, grad_thresh: float, split_thresh: float,
+                         mask: Optional[torch.Tensor] = None) -> int:
+        """:614-628.  NOTE the reference's test is on `torch.norm(grads, dim=-1)` of the 1-D statistic -- a scene-wide
+        scalar -- and is reproduced as such."""
+        if mask is None:
+            sel = torch.norm(grads, dim=-1) >= grad_thresh
+            sel = torch.logical_and(sel, self.svec_act.max(dim=1).values <= split_thresh)
+        else:
+            sel = mask
+        new = {name: self.params[name].detach()[sel] for name in self._field}
+        self.append(new)
+        return int(torch.count_nonzero(sel))
+
+    def densify_by_split(self, grads: Optional[torch.Tensor], grad_thresh: Optional[float], split_thresh: float,
+                         n_splits: int = 2, split_shrink: float = 0.8, mask: Optional[torch.Tensor] = None,
+                         noise: Optional[torch.Tensor] = None) -> int:
+        """:551-612.  `noise` [n_selected * n_splits, 3] replaces the reference's `torch.randn` (pass it for
+        reproducible / rank-identical splits; drawn on the store's device otherwise)."""
+        if mask is not None:
+            sel = mask
+        else:
+            padded = torch.zeros(self.N, device=self.device)
+            padded[: grads.shape[0]] = grads.reshape(-1)
+            sel = torch.logical_and(padded >= grad_thresh, self.svec_act.max(dim=1).values > split_thresh)
+        n_sel = int(torch.count_nonzero(sel))
+        rep = lambda t: t.detach()[sel].repeat(n_splits, *([1] * (t.dim() - 1)))
+        new_mean, new_qvec = rep(self.params["mean"]), rep(self.params["qvec"])
+        new_svec = torch.exp(rep(self.params["svec"]))
+        if noise is None:
+            noise = torch.randn(n_sel * n_splits, 3, device=self.device)
+        gn = noise.to(self.device) * new_svec
+        rot_t = quat_to_rotmat(new_qvec).transpose(-1, -2)  # the reference multiplies by the TRANSPOSE (:575-580)
+        new = {"mean": new_mean + torch.einsum("bij,bj->bi", rot_t, gn), "qvec": new_qvec,
+               "svec": torch.log(new_svec / (n_splits * split_shrink))}
+        for name in self._field:
+            if name not in new:
+                new[name] = rep(self.params[name])
+        self.append(new)
+        prune_mask = torch.cat((sel, torch.zeros(n_splits * n_sel, dtype=torch.bool, device=self.device)))
+        self.prune_by_mask(prune_mask)
+        return n_sel
+
+    def densify_by_scale(self, scale_max: float, split_thresh: float, n_splits: int = 2, split_shrink: float = 0.8,
+                         noise=None) -> int:
+        """:630-632"""
+        return self.densify_by_split(None, None, split_thresh, n_splits, split_shrink,
+                                     mask=(self.svec_act > scale_max).any(dim=-1), noise=noise)
+
+    def densify_official(self, mean2d_thresh: float, split_thresh: float, n_splits: int = 2,
+                         split_shrink: float = 0.8, noise=None):
+        """`densify()` with type "official" (:770-778, conf/renderer/regular.yaml:29-39): clone, then split with the
+        clone-time statistic zero-padded, then reset the accumulators (:816-817)."""
+        grads = self.mean_2d_grad_accum / self.cnt
+        grads[grads.isnan()] = 0.0
+        n_clone = self.densify_by_clone(grads, mean2d_thresh, split_thresh)
+        n_split = self.densify_by_split(grads, mean2d_thresh, split_thresh, n_splits, split_shrink, noise=noise)
+        self.reset_densify_info()
+        return n_clone, n_split
+
+    def prune(self, radii2d_thresh: float = 0.0, alpha_thresh: float = 0.0, radii3d_thresh: float = 0.0):
+        """`prune()` (:1152-1176) with the thresholds already evaluated for the step: by screen radius, then by
+        opacity, then by 3-D scale, each on the survivors of the previous one."""
+        n_scale = n_alpha = n_svec = 0
+        if radii2d_thresh > 0.0:
+            n_scale = self.prune_by_mask(self.max_radii2d > radii2d_thresh)
+        if alpha_thresh > 0.0:
+            n_alpha = self.prune_by_mask(self.alpha_act.reshape(self.N) < alpha_thresh)
+        if radii3d_thresh > 0.0:
+            n_svec = self.prune_by_mask((self.svec_act > radii3d_thresh).all(dim=-1))
+        return n_scale, n_alpha, n_svec

@@ -95,3 +95,41 @@ def test_view_sharded_allreduce_matches_single_process(oracle_mod):
     # .grad of every parameter is a view of the flat buffer (no pack pass before the collective)
     for name, p in single.params.items():
         assert p.grad.data_ptr() == single.grad_views[name].data_ptr()
+
+
+def _store_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gsgen_b200.store import GaussianStore
+
+        g = torch.Generator().manual_seed(5)
+        N = 40
+        params = dict(mean=torch.randn(N, 3, generator=g), qvec=torch.randn(N, 4, generator=g),
+                      svec=torch.randn(N, 3, generator=g), alpha=torch.randn(N, generator=g),
+                      color=torch.randn(N, 3, generator=g))
+        for cap in (None, 64):  # full arena: one flat collective; spare capacity: live rows only
+            st = GaussianStore(params, None, "cpu", capacity=cap)
+            st.zero_grad()
+            loss = sum(((rank + 1.0) * (i + 1) * p).sum() for i, p in enumerate(st.params.values()))
+            loss.backward()
+            st.all_reduce()
+            for i, (name, gv) in enumerate(st.grad_views.items()):
+                assert torch.equal(gv, torch.full_like(gv, 3.0 * (i + 1))), (cap, name)  # (1 + 2) * (i + 1)
+            if cap is not None:  # dead rows were neither sent nor touched
+                for name in st.grad_views:
+                    assert float(st._rows(st.flat_grad, name, st.cap - st.N, st.N).abs().max()) == 0.0
+        if rank == 0:
+            ret["ok"] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_store_allreduce_sums_live_rows_only():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_store_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret.get("ok")
