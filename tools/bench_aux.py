@@ -21,7 +21,7 @@ from gsgen_b200.scenes import make_scene  # noqa: E402
 DEV = "cuda"
 
 
-def timeit(fn, reps=20, warm=5):
+def timeit(fn, reps=10, warm=3):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -85,8 +85,8 @@ def main():
         render_view(m, q, torch.exp(s), torch.sigmoid(a), c2w, cam, sh=sh, C=4)["rgb"].backward(gradient=w)
 
     lv = leaves()
-    mf, bf = timeit(fused, reps=15, warm=4)
-    mt, bt = timeit(torch_act, reps=15, warm=4)
+    mf, bf = timeit(fused, reps=8, warm=3)
+    mt, bt = timeit(torch_act, reps=8, warm=3)
     res["view_c3_raw_leaves"] = {"ms_median_in_kernel_activations": mf, "ms_median_torch_activations": mt,
                                  "ms_min_in_kernel": bf, "ms_min_torch": bt}
     print(json.dumps(res, indent=1))
