@@ -353,6 +353,112 @@ def last_rgb_of(vpr, mine, render_view, c2ws_cpu, cams, C, slot_of, h_c2w, v0):
     return out["rgb"]
 
 
+def measure_e2e(args, vpr, mine, render_view, c2ws_cpu, cams, gouts, C, slot_of, N, n_views, world, dev, barrier):
+    """The metric through the public API with HOST buffers: every step copies the upstream gradient image from pinned
+    host memory (H2D), renders + back-propagates through render_view(), and copies the rendered image to pinned host
+    memory (D2H).  Measured twice: everything on the launching stream, and with the two copies on side streams."""
+    import torch.distributed as dist
+
+    v0 = mine[0]
+    H, W = cams[v0].h, cams[v0].w
+    h_c2w = c2ws_cpu[v0].clone().pin_memory()
+    h_gout = gouts[v0].cpu().pin_memory()
+    h_rgb = torch.empty(H, W, 3).pin_memory()
+    d_gout = torch.empty_like(gouts[v0])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def view_args(v):
+        return (vpr.params["mean"], vpr.params["qvec"], vpr.params["svec"], vpr.params["alpha"],
+                h_c2w if v == v0 else c2ws_cpu[v], cams[v])
+
+    def e2e_step_serial(i):
+        vpr.zero_grad()
+        for v in mine:
+            d_gout.copy_(h_gout, non_blocking=True)
+            out = render_view(*view_args(v), sh=vpr.params["sh"], C=C, slot=slot_of[v], grad_sink=vpr.grad_views)
+            out["rgb"].backward(gradient=d_gout)
+            h_rgb.copy_(out["rgb"].detach(), non_blocking=True)
+        vpr.all_reduce()
+
+    # Same bytes, same calls, but the two copies ride their own streams: the upstream-gradient H2D of a view
+    # overlaps that view's forward, the image D2H overlaps its backward (PCIe is full duplex; the copy engines
+    # are independent of the SMs).  Every step still moves both buffers and the loop ends with all streams joined.
+    cs_in, cs_out = torch.cuda.Stream(), torch.cuda.Stream()
+    d_gout2 = [torch.empty_like(d_gout), torch.empty_like(d_gout)]
+    ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_img = torch.cuda.Event()
+    n_copy = [0]
+
+    def e2e_step_pipelined(i):
+        main = torch.cuda.current_stream()
+        vpr.zero_grad()
+        for v in mine:
+            k = n_copy[0] & 1
+            n_copy[0] += 1
+            with torch.cuda.stream(cs_in):
+                cs_in.wait_event(ev_free[k])  # the backward that last read this buffer is done
+                d_gout2[k].copy_(h_gout, non_blocking=True)
+                ev_in[k].record(cs_in)
+            out = render_view(*view_args(v), sh=vpr.params["sh"], C=C, slot=slot_of[v], grad_sink=vpr.grad_views)
+            rgb = out["rgb"]
+            ev_img.record(main)
+            with torch.cuda.stream(cs_out):
+                cs_out.wait_event(ev_img)
+                h_rgb.copy_(rgb.detach(), non_blocking=True)
+            rgb.record_stream(cs_out)
+            main.wait_event(ev_in[k])
+            rgb.backward(gradient=d_gout2[k])
+            ev_free[k].record(main)
+        vpr.all_reduce()
+
+    def e2e_measure(step_fn):
+        for i in range(3):
+            step_fn(i)
+        runs_ = []
+        for _ in range(3):  # best of three K-step loops, like the device-resident number (host CFS throttling)
+            barrier(); torch.cuda.synchronize()
+            e0.record()
+            for i in range(args.steps):
+                step_fn(i)
+            main = torch.cuda.current_stream()
+            main.wait_stream(cs_in); main.wait_stream(cs_out)  # the step's copies belong to the timed region
+            e1.record()
+            torch.cuda.synchronize(); barrier()
+            t2 = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+            if world > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            runs_.append(float(t2.item()))
+        return runs_
+
+    serial_runs = e2e_measure(e2e_step_serial)
+    mode, e2e_runs, pipe_err = "copies on the launching stream", serial_runs, None
+    if world == 1:  # the side-stream schedule was validated on one GPU only in round 1
+        try:
+            pipe_runs = e2e_measure(e2e_step_pipelined)
+            torch.cuda.synchronize()
+            # the image that reached the host must be the image the device holds
+            ref_img = last_rgb_of(vpr, mine, render_view, c2ws_cpu, cams, C, slot_of, h_c2w, v0)
+            img_diff = float((h_rgb.to(dev) - ref_img).abs().max())
+            if img_diff != 0.0:
+                raise RuntimeError(f"side-stream D2H image differs from the device image by {img_diff}")
+            mode, e2e_runs = "copies on side streams (H2D under the forward, D2H under the backward)", pipe_runs
+        except Exception as ex:  # report the single-stream number rather than no number
+            pipe_err = repr(ex)
+    else:
+        pipe_err = "not enabled for world_size > 1"
+    ms_e2e = min(e2e_runs)
+    bi = len(mine) * (h_gout.numel() * 4 + 240)  # gradient image + the by-value camera struct
+    bo = len(mine) * h_rgb.numel() * 4
+    return {"value": n_views * N * H * W / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
+            "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo, "ms_per_step_all_runs": e2e_runs,
+            "copy_schedule": mode, "ms_per_step_single_stream": min(serial_runs),
+            "ms_per_step_single_stream_all_runs": serial_runs, "side_stream_error": pipe_err,
+            "what": "render_view()+backward through the public API; per step: host camera pose (by-value kernel "
+                    "argument) + pinned upstream gradient image H2D, rendered image D2H to pinned memory; Gaussian "
+                    "parameters stay resident (they are the model state, like weights)"}
+
+
 def run_ours(args):
     import ctypes
 
@@ -502,105 +608,11 @@ def run_ours(args):
     # (camera pose + upstream gradient image) and D2H of the rendered image
     e2e = None
     if not args.no_e2e:
-        v0 = mine[0]
-        h_c2w = c2ws_cpu[v0].clone().pin_memory()
-        h_gout = gouts[v0].cpu().pin_memory()
-        h_rgb = torch.empty(H, W, 3).pin_memory()
-        d_gout = torch.empty_like(gouts[v0])
-
-        def e2e_step_serial(i):
-            vpr.zero_grad()
-            for v in mine:
-                d_gout.copy_(h_gout, non_blocking=True)
-                out = render_view(vpr.params["mean"], vpr.params["qvec"], vpr.params["svec"], vpr.params["alpha"],
-                                  h_c2w if v == v0 else c2ws_cpu[v], cams[v], sh=vpr.params["sh"], C=C,
-                                  slot=slot_of[v], grad_sink=vpr.grad_views)
-                out["rgb"].backward(gradient=d_gout)
-                h_rgb.copy_(out["rgb"].detach(), non_blocking=True)
-            vpr.all_reduce()
-
-        # Same bytes, same calls, but the two copies ride their own streams: the upstream-gradient H2D of a view
-        # overlaps that view's forward, the image D2H overlaps its backward (PCIe is full duplex; the copy engines
-        # are independent of the SMs).  Every step still moves both buffers and the loop ends with all streams joined.
-        cs_in, cs_out = torch.cuda.Stream(), torch.cuda.Stream()
-        d_gout2 = [torch.empty_like(d_gout), torch.empty_like(d_gout)]
-        ev_in = [torch.cuda.Event(), torch.cuda.Event()]
-        ev_free = [torch.cuda.Event(), torch.cuda.Event()]
-        ev_img = torch.cuda.Event()
-        n_copy = [0]
-
-        def e2e_step_pipelined(i):
-            main = torch.cuda.current_stream()
-            vpr.zero_grad()
-            for v in mine:
-                k = n_copy[0] & 1
-                n_copy[0] += 1
-                with torch.cuda.stream(cs_in):
-                    cs_in.wait_event(ev_free[k])  # the backward that last read this buffer is done
-                    d_gout2[k].copy_(h_gout, non_blocking=True)
-                    ev_in[k].record(cs_in)
-                out = render_view(vpr.params["mean"], vpr.params["qvec"], vpr.params["svec"], vpr.params["alpha"],
-                                  h_c2w if v == v0 else c2ws_cpu[v], cams[v], sh=vpr.params["sh"], C=C,
-                                  slot=slot_of[v], grad_sink=vpr.grad_views)
-                rgb = out["rgb"]
-                ev_img.record(main)
-                with torch.cuda.stream(cs_out):
-                    cs_out.wait_event(ev_img)
-                    h_rgb.copy_(rgb.detach(), non_blocking=True)
-                rgb.record_stream(cs_out)
-                main.wait_event(ev_in[k])
-                rgb.backward(gradient=d_gout2[k])
-                ev_free[k].record(main)
-            vpr.all_reduce()
-
-        def e2e_measure(step_fn):
-            for i in range(3):
-                step_fn(i)
-            runs_ = []
-            for _ in range(3):  # best of three K-step loops, like the device-resident number (host CFS throttling)
-                barrier(); torch.cuda.synchronize()
-                e0.record()
-                for i in range(args.steps):
-                    step_fn(i)
-                main = torch.cuda.current_stream()
-                main.wait_stream(cs_in); main.wait_stream(cs_out)  # the step's copies belong to the timed region
-                e1.record()
-                torch.cuda.synchronize(); barrier()
-                t2 = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
-                if world > 1:
-                    dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-                runs_.append(float(t2.item()))
-            return runs_
-
-        serial_runs = e2e_measure(e2e_step_serial)
-        mode, e2e_runs, pipe_err = "serial", serial_runs, None
-        ok = torch.ones(1, device=dev)
         try:
-            if world > 1:  # validated on one GPU only in round 1; multi-rank keeps the single-stream schedule
-                raise RuntimeError("side-stream schedule not enabled for world_size > 1")
-            pipe_runs = e2e_measure(e2e_step_pipelined)
-            torch.cuda.synchronize()
-            # the image that reached the host must be the image the device holds
-            img_diff = float((h_rgb.to(dev) - last_rgb_of(vpr, mine, render_view, c2ws_cpu, cams, C, slot_of, h_c2w, v0)).abs().max())
-            if img_diff != 0.0:
-                raise RuntimeError(f"pipelined D2H image differs from the device image by {img_diff}")
-        except Exception as ex:  # report the serial number rather than no number
-            pipe_err = repr(ex)
-            ok.zero_()
-        if world > 1:
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if float(ok.item()) > 0:
-            mode, e2e_runs = "copies on side streams (H2D under the forward, D2H under the backward)", pipe_runs
-        ms_e2e = min(e2e_runs)
-        bi = len(mine) * (h_gout.numel() * 4 + 240)  # gradient image + the by-value camera struct
-        bo = len(mine) * h_rgb.numel() * 4
-        e2e = {"value": n_views * scene.N * H * W / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo, "ms_per_step_all_runs": e2e_runs,
-               "copy_schedule": mode, "ms_per_step_single_stream": min(serial_runs),
-               "ms_per_step_single_stream_all_runs": serial_runs, "side_stream_error": pipe_err,
-               "what": "render_view()+backward through the public API; per step: host camera pose (by-value kernel "
-                       "argument) + pinned upstream gradient image H2D, rendered image D2H to pinned memory; Gaussian "
-                       "parameters stay resident (they are the model state, like weights)"}
+            e2e = measure_e2e(args, vpr, mine, render_view, c2ws_cpu, cams, gouts, C, slot_of, scene.N, n_views,
+                              world, dev, barrier)
+        except Exception as ex:  # the bench line must still print; every rank takes the same branch
+            e2e = {"value": None, "unit": UNIT, "error": repr(ex)}
 
     if rank != 0:
         if world > 1:
