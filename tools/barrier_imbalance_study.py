@@ -55,6 +55,9 @@ def main():
     sample = rng.choice(nonempty, size=min(args.tiles, len(nonempty)), replace=False)
     B = args.batch
     tot = dict(sync=0.0, decoupled=0.0, balanced=0.0, hits=0, entries=0)
+    pairings = {"opposite (i, 7-i)": [(0, 7), (1, 6), (2, 5), (3, 4)], "half-tile (i, i+4)": [(0, 4), (1, 5), (2, 6), (3, 7)],
+                "neighbour (2i, 2i+1)": [(0, 1), (2, 3), (4, 5), (6, 7)]}
+    pair_stat = {k: dict(busiest=0.0, mean=0.0, both=0, either=0) for k in pairings}
     lx, ly = np.meshgrid(np.arange(16), np.arange(16))
     for tile in sample:
         ty, tx = divmod(int(tile), tw)
@@ -67,17 +70,24 @@ def main():
         work = []  # per batch: hits per warp [8]
         for b0 in range(0, len(g), B):
             wb = np.zeros(8)
+            per_entry = []
             for gi in g[b0:b0 + B]:
                 dx, dy = px - mean2d[gi, 0], py - mean2d[gi, 1]
                 q = inv[gi, 0] * dx * dx + (inv[gi, 1] + inv[gi, 2]) * dx * dy + inv[gi, 3] * dy * dy
                 aG = alpha[gi] * np.exp(-0.5 * q)
                 ok = (~done) & (aG >= 1.0 / 255.0)
                 # which warps (8x4 blocks: warp = 2*(row//4) + col//8) walk this entry
-                okw = ok.reshape(4, 4, 2, 8).any(axis=(1, 3)).reshape(-1)  # [row block 4][col block 2]
+                okw = ok.reshape(4, 4, 2, 8).any(axis=(1, 3)).reshape(-1)  # [row block 4][col block 2] = warp index
                 wb += okw
+                per_entry.append(okw)
                 T = np.where(ok, T * (1.0 - aG), T)
                 done |= ok & (T < 1e-4)
             work.append(wb)
+            pe = np.array(per_entry)
+            for name, pairs in pairings.items():
+                for a_, b_ in pairs:
+                    pair_stat[name]["both"] += int((pe[:, a_] & pe[:, b_]).sum())
+                    pair_stat[name]["either"] += int((pe[:, a_] | pe[:, b_]).sum())
             tot["entries"] += len(g[b0:b0 + B])
             if done.all():
                 break
@@ -86,12 +96,21 @@ def main():
         tot["decoupled"] += work.sum(axis=0).max()
         tot["balanced"] += work.sum(axis=0).mean()
         tot["hits"] += work.sum()
+        per_warp = work.sum(axis=0)
+        for name, pairs in pairings.items():
+            ps = np.array([per_warp[a_] + per_warp[b_] for a_, b_ in pairs])
+            pair_stat[name]["busiest"] += ps.max()
+            pair_stat[name]["mean"] += ps.mean()
     print(f"{args.workload}: {len(sample)} tiles, batch {B}: staged entries/tile {tot['entries'] / len(sample):.0f}, "
           f"warp-hits/tile {tot['hits'] / len(sample):.0f}")
     print(f"  schedule length in warp-hits per tile: sync {tot['sync'] / len(sample):.1f}  decoupled "
           f"{tot['decoupled'] / len(sample):.1f}  balanced {tot['balanced'] / len(sample):.1f}")
     print(f"  sync / decoupled = {tot['sync'] / tot['decoupled']:.3f}   sync / balanced = {tot['sync'] / tot['balanced']:.3f}"
           f"   decoupled / balanced = {tot['decoupled'] / tot['balanced']:.3f}")
+    print("  two pixel blocks per warp (4 warps per tile): busiest pair / mean pair, and share of walked entries that "
+          "both blocks of a pair blend (one shared-memory read serves two)")
+    for name, st in pair_stat.items():
+        print(f"    {name:22s} busiest/mean {st['busiest'] / st['mean']:.3f}   both/either {st['both'] / max(st['either'], 1):.3f}")
 
 
 if __name__ == "__main__":
