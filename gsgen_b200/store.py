@@ -149,6 +149,27 @@ class GaussianStore:
             for name in self._field:
                 dist.all_reduce(self._rows(self.flat_grad, name, self.N), op=dist.ReduceOp.SUM, group=self.group)
 
+    # ---- checkpoint view (gs/gaussian_splatting.py:294-339) -------------------------------------------------
+    def get_params_for_save(self) -> Dict[str, torch.Tensor]:
+        """The raw leaves under the reference's checkpoint keys (`Trainer.save` stores them as ckpt["params"],
+        trainer.py:255-266; optimizer state is not part of a reference checkpoint).  Detached CPU copies, so a saved
+        checkpoint does not alias the arena; `gsgen_b200.export` and `GaussianStore.load` take this dict."""
+        return {name: p.detach().to("cpu").clone() for name, p in self.params.items()}
+
+    @classmethod
+    def load(cls, ckpt, C: Optional[int] = None, device=None, **kw) -> "GaussianStore":
+        """From a reference checkpoint: a path / dict with "params" (trainer checkpoint) or the params dict itself
+        (renderer-only checkpoint, :318-331).  Keys other than the Gaussian fields (cfg, bg, ...) are ignored."""
+        if not isinstance(ckpt, dict):
+            ckpt = torch.load(ckpt, map_location="cpu")
+        if "params" in ckpt:
+            ckpt = ckpt["params"]
+        names = [n for n, _, _, _ in field_layout(1, C)]
+        missing = [n for n in names if n not in ckpt]
+        if missing:
+            raise RuntimeError(f"checkpoint lacks {missing}")
+        return cls({n: ckpt[n] for n in names}, C, device, **kw)
+
     # ---- densification statistics (gs/gaussian_splatting.py:464-479) ---------------------------------------
     def reset_densify_info(self):
         z = lambda: torch.zeros(self.N, dtype=torch.float32, device=self.device)

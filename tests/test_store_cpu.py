@@ -124,3 +124,19 @@ def test_quat_to_rotmat_is_a_rotation_and_normalises():
     assert torch.allclose(R @ R.transpose(-1, -2), torch.eye(3).expand(64, 3, 3), atol=1e-5)
     assert torch.allclose(torch.linalg.det(R), torch.ones(64), atol=1e-5)
     assert torch.allclose(R, quat_to_rotmat(q / q.norm(dim=-1, keepdim=True)), atol=1e-6)
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    gold = _load()
+    st = _store_from(gold, "s0", capacity=1000)
+    saved = st.get_params_for_save()
+    assert set(saved) == set(FIELDS) and all(not v.requires_grad for v in saved.values())
+    saved["mean"][0, 0] += 1.0  # a checkpoint does not alias the arena
+    assert float(st.params["mean"][0, 0]) != float(saved["mean"][0, 0])
+    path = str(tmp_path / "step_10.pt")
+    torch.save({"params": {**st.get_params_for_save(), "cfg": {"x": 1}, "bg": {}}, "cfg": {}, "step": 10}, path)
+    st2 = GaussianStore.load(path, None, "cpu")
+    for f in FIELDS:
+        assert torch.equal(st2.params[f].detach(), st.params[f].detach())
+    with pytest.raises(RuntimeError):
+        GaussianStore.load({"mean": saved["mean"]}, None, "cpu")
