@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# final single-GPU validation: what the driver runs at round end
+# single-GPU validation: what the driver runs at round end (tests, smoke, both bench arms)   gpurun --timeout 1500 -- bash tools/gpu_validate.sh
 set -u
 mkdir -p gpurun_out
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests/ -x -q -m gpu -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/pytest_gpu.log
