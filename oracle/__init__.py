@@ -13,9 +13,11 @@ Third-party arithmetic absent from /root/reference: kornia==0.6.0 (requirements.
 `kornia.geometry.conversions.quaternion_to_rotation_matrix(q, QuaternionCoeffOrder.WXYZ)`, called
 from utils/transforms.py:37.  kornia is not installed here and not vendored; `quat_to_rotmat`
 restates its published algorithm (normalise with eps 1e-12, then the standard unit-quaternion
-matrix).  No reference test pins that boundary ("parity unpinned" for non-unit quaternions);
-everything downstream of (mean2d, cov2d, depth) is pinned by tests/golden/ against the real
-reference `_gs` extension.
+matrix).  No reference artefact pins that boundary ("parity unpinned" for non-unit quaternions).
+Everything else is pinned: the torch stages by vectors the reference's OWN functions produced
+(tests/golden/make_pergaussian_golden.py executes project_gaussians / tile_culling_aabb_count /
+CameraInfo unmodified; tests/test_pergaussian_golden_cpu.py), everything downstream of
+(mean2d, cov2d, depth) by tests/golden/g*.npz from the real reference `_gs` extension.
 """
 from __future__ import annotations
 
