@@ -54,7 +54,7 @@ def main():
     compile_defs(f"{REF}/gs/culling.py", ["tile_culling_aabb_count"], ns)
 
     out = {}
-    for tag, cfg, N, reso in (("a", "c1", 2000, 200), ("b", "c3", 3000, 168)):
+    for tag, cfg, N, reso in (("a", "c1", 1200, 200), ("b", "c3", 1500, 168)):
         sc = make_scene(cfg, N=N, reso=reso)
         cam, c2w = sc.cams[0], sc.c2ws[0]
         rcam = ns["CameraInfo"](cam.fx, cam.fy, cam.cx, cam.cy, cam.w, cam.h, cam.near_plane, cam.far_plane)

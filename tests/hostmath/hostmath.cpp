@@ -130,4 +130,9 @@ void hm_adam(long long n, float* p, const float* g, float* m, float* v, double l
   const float step_size = (float)(lr / bc1);
   for (long long i = 0; i < n; ++i) adam_update(p[i], g[i], m[i], v[i], step_size, K);
 }
+
+// largest eigenvalue of cov2d as k_preprocess computes it for aux["radii2d"] (gs/gaussian_splatting.py:1240-1245)
+void hm_radius2d(int N, const float* cov2d, float* out) {
+  for (int i = 0; i < N; ++i) out[i] = radius2d(cov2d + 4 * i);
+}
 }
