@@ -240,8 +240,8 @@ class GaussianStore:
     def densify_by_split(self, grads: Optional[torch.Tensor], grad_thresh: Optional[float], split_thresh: float,
                          n_splits: int = 2, split_shrink: float = 0.8, mask: Optional[torch.Tensor] = None,
                          noise: Optional[torch.Tensor] = None) -> int:
-        """:551-612.  `noise` [n_selected * n_splits, 3] replaces the reference's `torch.randn` (pass it for
-        reproducible / rank-identical splits; drawn on the store's device otherwise)."""
+        """:551-612.  `noise` replaces the reference's `torch.randn`: a tensor [n_selected * n_splits, 3] or a callable
+        `n_rows -> tensor` (pass it for reproducible / rank-identical splits; drawn on the store's device otherwise)."""
         if mask is not None:
             sel = mask
         else:
@@ -254,6 +254,10 @@ class GaussianStore:
         new_svec = torch.exp(rep(self.params["svec"]))
         if noise is None:
             noise = torch.randn(n_sel * n_splits, 3, device=self.device)
+        elif callable(noise):
+            noise = noise(n_sel * n_splits)
+        if noise.shape[0] != n_sel * n_splits:
+            raise RuntimeError(f"split noise has {noise.shape[0]} rows, {n_sel * n_splits} are needed")
         gn = noise.to(self.device) * new_svec
         rot_t = quat_to_rotmat(new_qvec).transpose(-1, -2)  # the reference multiplies by the TRANSPOSE (:575-580)
         new = {"mean": new_mean + torch.einsum("bij,bj->bi", rot_t, gn), "qvec": new_qvec,
@@ -294,3 +298,45 @@ class GaussianStore:
         if radii3d_thresh > 0.0:
             n_svec = self.prune_by_mask((self.svec_act > radii3d_thresh).all(dim=-1))
         return n_scale, n_alpha, n_svec
+
+    # ---- the trainer-facing dispatchers (step gating as the reference) -------------------------------------
+    def densify_step(self, step: int, cfg) -> Optional[tuple]:
+        """`densify(step)` (gs/gaussian_splatting.py:751-817) for the non-legacy types this store implements: runs when
+        `cfg.enabled`, `warm_up <= step <= end` and `step % period == 0` (step_check(..., run_at_zero=True)); resets
+        the accumulators afterwards (:816-817).  cfg: mapping with the keys of conf/renderer/*.yaml `densify:`.
+        Returns the counts of the operation that ran, or None."""
+        from .renderer import step_check
+
+        get = cfg.get if hasattr(cfg, "get") else (lambda k, d=None: getattr(cfg, k, d))
+        if not get("enabled", False) or get("use_legacy", False):
+            return None
+        if step < get("warm_up") or step > get("end") or not step_check(step, get("period"), True):
+            return None
+        kind = get("type", "official")
+        if kind == "official":
+            res = self.densify_official(get("mean2d_thresh"), get("split_thresh"), get("n_splits", 2),
+                                        get("split_shrink", 0.8), noise=get("noise"))
+            return res  # densify_official already reset the accumulators
+        if kind == "scale":
+            n = self.densify_by_scale(get("scale_max"), get("split_thresh"), get("n_splits", 2),
+                                      get("split_shrink", 0.8), noise=get("noise"))
+        elif kind == "all":
+            n = self.densify_by_split(None, None, get("split_thresh"), 2, get("split_shrink", 0.8),
+                                      mask=torch.ones(self.N, dtype=torch.bool, device=self.device),
+                                      noise=get("noise"))
+        else:
+            raise NotImplementedError(f"densify type '{kind}' (K-nearest-neighbour variants are not built)")
+        self.reset_densify_info()
+        return (n,)
+
+    def prune_step(self, step: int, cfg) -> Optional[tuple]:
+        """`prune(step)` (:1152-1176): runs when `cfg.enabled`, `warm_up <= step <= end` and `step != 0 and
+        step % period == 0`; thresholds may be schedules in the reference (`C(value, step)`), pass numbers here."""
+        from .renderer import step_check
+
+        get = cfg.get if hasattr(cfg, "get") else (lambda k, d=None: getattr(cfg, k, d))
+        if not get("enabled", False):
+            return None
+        if step < get("warm_up") or step > get("end") or not step_check(step, get("period")):
+            return None
+        return self.prune(get("radii2d_thresh", 0.0), get("alpha_thresh", 0.0), get("radii3d_thresh", 0.0) or 0.0)

@@ -27,7 +27,8 @@ sys.path.insert(0, ROOT)
 REF = "/root/reference/gs/gaussian_splatting.py"
 METHODS = ["prune_optimizer", "densify_on_optimizer", "densify_with_new_params", "prune_by_mask", "densify_by_split",
            "densify_by_clone", "get_params_by_mask", "update_params_with_dict", "reset_densify_info",
-           "update_densify_info", "prune_by_scale", "prune_by_alpha", "prune_by_svec"]
+           "update_densify_info", "prune_by_scale", "prune_by_alpha", "prune_by_svec", "densify", "prune",
+           "densify_by_scale", "densify_by_all"]
 
 
 class TorchProxy:
@@ -96,13 +97,25 @@ def snapshot(h, tag, out):
     out[f"{tag}_N"] = torch.tensor([h.N])
 
 
+def step_check(step, step_size, run_at_zero=False):  # gs/renderer.py:27-31 (checked in tests/test_host_mirrors_cpu.py)
+    if step_size == 0:
+        return False
+    return (run_at_zero or step != 0) and step % step_size == 0
+
+
+class Cfg(dict):
+    """OmegaConf stand-in: attribute and .get access"""
+    __getattr__ = dict.__getitem__
+
+
 def main():
     import oracle
 
     g = torch.Generator().manual_seed(77)
     noise_log = []
     ns = {"torch": TorchProxy(g, noise_log), "nn": nn, "qvec2rotmat_batched": oracle.quat_to_rotmat,
-          "C": lambda v, step, _=None: v,
+          "C": lambda v, step, _=None: v, "step_check": step_check,
+          "console": type("Con", (), {"print": staticmethod(lambda *a, **k: None)})(),
           "field2raw": dict(mean="mean", qvec="qvec", svec="svec_before_activation", color="color_before_activation",
                             alpha="alpha_before_activation")}
     for name, fn in load_methods(ns).items():
@@ -154,6 +167,40 @@ def main():
     n3 = h.prune_by_svec(0)
     snapshot(h, "s5", out)
     out["prune_counts"] = torch.tensor([n1, n2, n3])
+    # ---- the step-gated dispatchers densify(step) / prune(step) (:751-817, :1152-1176) on a fresh copy of s0
+    h2 = Host()
+    h2.N = N
+    for f, raw in ns["field2raw"].items():
+        setattr(h2, raw, nn.Parameter(out[f"s0_{f}"].clone()))
+    h2.optimizer = torch.optim.Adam(
+        [{"params": [getattr(h2, ns["field2raw"][f])], "lr": lr[f], "name": f} for f in Host.fields], lr=0.0, eps=1e-15)
+    for f in Host.fields:  # same moments as s0
+        p_ = getattr(h2, ns["field2raw"][f])
+        h2.optimizer.state[p_] = {"step": torch.tensor(3.0), "exp_avg": out[f"s0_{f}_exp_avg"].clone(),
+                                  "exp_avg_sq": out[f"s0_{f}_exp_avg_sq"].clone()}
+    h2.densify_cfg = Cfg(enabled=True, type="official", warm_up=2000, end=4999, period=500, mean2d_thresh=0.02,
+                         split_thresh=0.02, n_splits=2, split_shrink=0.8, use_legacy=False)
+    h2.prune_cfg = Cfg(enabled=True, warm_up=0, end=15000, period=100, radii2d_thresh=1.0, alpha_thresh=0.05,
+                       radii3d_thresh=0.012)
+    h2.cfg = Cfg(densify=h2.densify_cfg)
+    trace = []
+    g2 = torch.Generator().manual_seed(78)
+    noise2 = []
+    ns["torch"]._gen, ns["torch"]._log = g2, noise2
+    for step in (0, 1999, 2000, 2100, 2500, 5000):
+        h2.mean_2d_grad_accum = out["s0_mean_2d_grad_accum"].clone()[: h2.N] if h2.N <= N else torch.rand(h2.N, generator=g) * 0.1
+        h2.cnt = out["s0_cnt"].clone()[: h2.N] if h2.N <= N else torch.ones(h2.N)
+        h2.max_radii2d = torch.linspace(0.0, 1.3, h2.N)
+        n_before = h2.N
+        h2.densify(step, verbose=False)
+        n_mid = h2.N
+        h2.max_radii2d = torch.linspace(0.0, 1.3, h2.N)
+        h2.prune(step, verbose=False)
+        trace.append([step, n_before, n_mid, h2.N])
+    out["dispatch_trace"] = torch.tensor(trace)
+    out["dispatch_noise"] = torch.cat(noise2) if noise2 else torch.zeros(0, 3)
+    snapshot(h2, "s9", out)
+    print("dispatch trace (step, N before, N after densify, N after prune):", trace)
     path = os.path.join(ROOT, "tests", "golden", "densify_official.npz")
     np.savez_compressed(path, **{k: v.numpy() for k, v in out.items()})
     print("N0", N, "clone", n_clone, "split", n_split, "-> N", int(out["s2_N"]), "prune", n1, n2, n3, "-> N", h.N,

@@ -132,7 +132,7 @@ def test_checkpoint_roundtrip(tmp_path):
     saved = st.get_params_for_save()
     assert set(saved) == set(FIELDS) and all(not v.requires_grad for v in saved.values())
     saved["mean"][0, 0] += 1.0  # a checkpoint does not alias the arena
-    assert float(st.params["mean"][0, 0]) != float(saved["mean"][0, 0])
+    assert float(st.params["mean"].detach()[0, 0]) != float(saved["mean"][0, 0])
     path = str(tmp_path / "step_10.pt")
     torch.save({"params": {**st.get_params_for_save(), "cfg": {"x": 1}, "bg": {}}, "cfg": {}, "step": 10}, path)
     st2 = GaussianStore.load(path, None, "cpu")
@@ -140,3 +140,42 @@ def test_checkpoint_roundtrip(tmp_path):
         assert torch.equal(st2.params[f].detach(), st.params[f].detach())
     with pytest.raises(RuntimeError):
         GaussianStore.load({"mean": saved["mean"]}, None, "cpu")
+
+
+def test_step_gated_dispatchers_follow_the_reference_trace():
+    """densify(step) / prune(step) of the reference (gs/gaussian_splatting.py:751-817, :1152-1176), run by the fixture
+    generator over six steps around the warm-up / period / end boundaries: same N after every call, same final rows."""
+    gold = _load()
+    st = _store_from(gold, "s0")
+    dens = dict(enabled=True, type="official", warm_up=2000, end=4999, period=500, mean2d_thresh=0.02, split_thresh=0.02,
+                n_splits=2, split_shrink=0.8, use_legacy=False)
+    prun = dict(enabled=True, warm_up=0, end=15000, period=100, radii2d_thresh=1.0, alpha_thresh=0.05,
+                radii3d_thresh=0.012)
+    pool = {"at": 0}
+
+    def noise(n):
+        out = gold["dispatch_noise"][pool["at"]: pool["at"] + n]
+        pool["at"] += n
+        return out
+
+    dens["noise"] = noise
+    for step, n_before, n_mid, n_after in gold["dispatch_trace"].tolist():
+        assert st.N == n_before
+        st.mean_2d_grad_accum = gold["s0_mean_2d_grad_accum"].clone()[: st.N]
+        st.cnt = gold["s0_cnt"].clone()[: st.N]
+        st.max_radii2d = torch.linspace(0.0, 1.3, st.N)
+        st.densify_step(step, dens)
+        assert st.N == n_mid, (step, st.N, n_mid)
+        st.max_radii2d = torch.linspace(0.0, 1.3, st.N)
+        st.prune_step(step, prun)
+        assert st.N == n_after, (step, st.N, n_after)
+    assert pool["at"] == gold["dispatch_noise"].shape[0]
+    _check_rows_only(st, gold, "s9")
+
+
+def _check_rows_only(st, gold, tag):
+    for f in FIELDS:
+        n = st.N
+        for buf, suffix in ((st.flat_param, ""), (st.exp_avg, "_exp_avg"), (st.exp_avg_sq, "_exp_avg_sq")):
+            ours, ref = st._rows(buf, f, n), gold[f"{tag}_{f}{suffix}"].reshape(n, -1)
+            assert torch.allclose(ours, ref, rtol=1e-5, atol=1e-6), (f, suffix, float((ours - ref).abs().max()))
