@@ -116,6 +116,8 @@ class FlatAdam:
     def step(self, train_step: int = None, grad_scale: float = 1.0):
         """One Adam update.  `train_step` is the trainer's step counter the schedules are evaluated at (defaults to
         the number of updates done so far, i.e. update_lr(step) followed by optimizer.step())."""
+        if train_step is None:  # the trainer's step set by GaussianSplattingRenderer.update(step), else the update count
+            train_step = getattr(self, "train_step", None)
         if train_step is None:
             train_step = self.n_steps
         lrs = self.lr_at(train_step)

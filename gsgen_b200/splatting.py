@@ -1,0 +1,192 @@
+"""`GaussianSplattingRenderer` as the reference's trainer sees it ("autograd surface above"), built
+from the pieces of this package:
+
+    reference (gs/gaussian_splatting.py)                         here
+    ---------------------------------------------------------    ------------------------------------------------------
+    raw leaves as nn.Parameters, activations in properties       `GaussianStore` capacity arena (raw leaves are views of it)
+    render_one: ~60 torch kernels + 5 `_gs` calls per view       `rasterizer.render_view(raw_params=True, grad_sink=...)`
+    forward(batch): sequential views, stack_dicts (:1426-1460)   `__call__(batch)`
+    set_optimizer / update_lr: torch Adam, one group per field   `FlatAdam` over the arena, per-field lr schedules
+    post_backward -> update_densify_info (:464-469, :1471-1476)  `post_backward()`
+    densify(step) / prune(step) with optimizer surgery           `store.densify_step / prune_step` (row operations)
+    get_params_for_save / load (:294-339)                        same keys
+
+The trainer loop of the reference (`trainer.py:575-617`) then reads:
+
+    renderer.update(step); out = renderer(batch, use_bg, rgb_only); loss.backward()
+    renderer.optimizer.step(); renderer.post_backward(); renderer.densify(step); renderer.prune(step)
+    renderer.optimizer.zero_grad()
+
+Only the default configuration of the reference is covered: exp / sigmoid / sigmoid activations, RGB colours (no PBR
+shading, no learned normals), a constant or per-pixel background.  `render_fn` exists so that this host logic can be
+exercised without a GPU (the test-suite plugs in the CPU oracle); the default is the CUDA path and there is no
+fallback.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Sequence
+
+import torch
+
+from .store import GaussianStore
+
+FIELDS = ("mean", "qvec", "svec", "color", "alpha")  # self.fields of the reference (:241-258)
+
+
+def _get(cfg, key, default=None):
+    if cfg is None:
+        return default
+    if hasattr(cfg, "get"):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+def stack_dicts(dicts: Sequence[Dict[str, torch.Tensor]]) -> Dict[str, torch.Tensor]:
+    """utils/misc.py:180-184"""
+    return {k: torch.stack([d[k] for d in dicts], dim=0) for k in dicts[0].keys()}
+
+
+class GaussianSplattingRenderer:
+    """cfg: mapping with the renderer keys the hot path consumes (conf/renderer/base.yaml): tile_size (16),
+    frustum_culling_radius, tile_culling_radius, T_thresh, depth_detach, skip_frustum_culling, densify{...},
+    prune{...}.  initial_values: {"mean","qvec","svec","color","alpha"[, "raw"]} -- activated values unless raw
+    (initialize(), :166-191)."""
+
+    def __init__(self, cfg, initial_values: Dict[str, torch.Tensor], device="cuda", capacity: Optional[int] = None,
+                 background=None, render_fn: Optional[Callable] = None, group=None):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if _get(cfg, "tile_size", 16) != 16:
+            raise RuntimeError("tile_size must be 16")
+        for key, want in (("svec_act", "exp"), ("alpha_act", "sigmoid"), ("color_act", "sigmoid")):
+            if _get(cfg, key, want) != want:
+                raise NotImplementedError(f"{key}={_get(cfg, key)}: the fused front end implements {want}")
+        raw = bool(initial_values.get("raw", False))
+        f32 = lambda t: torch.as_tensor(t, dtype=torch.float32)
+        leaves = {"mean": f32(initial_values["mean"]), "qvec": f32(initial_values["qvec"])}
+        svec, color, alpha = f32(initial_values["svec"]), f32(initial_values["color"]), f32(initial_values["alpha"])
+        leaves["svec"] = svec if raw else torch.log(svec)              # inv_activations["exp"]
+        leaves["color"] = color if raw else torch.logit(color)         # inv_activations["sigmoid"]
+        leaves["alpha"] = (alpha if raw else torch.logit(alpha)).reshape(-1)
+        self.store = GaussianStore(leaves, None, self.device, capacity=capacity, group=group)
+        self.background = background  # None (black), a [3] tensor, or callable(rays_d[H,W,3]) -> [H,W,3]
+        self.training = True
+        self.step = 0
+        self.optimizer = None
+        self._lr_cfg = None
+        self._pending = []  # (mask, aux) of the views rendered since the last post_backward
+        if render_fn is None:
+            from .rasterizer import render_view as render_fn  # the CUDA path; raises without libgsb200.so / a GPU
+        self._render_fn = render_fn
+
+    # ---- the attributes the reference exposes ------------------------------------------------------------
+    @property
+    def N(self) -> int:
+        return self.store.N
+
+    mean = property(lambda self: self.store.params["mean"])
+    qvec = property(lambda self: self.store.params["qvec"])
+    svec_before_activation = property(lambda self: self.store.params["svec"])
+    color_before_activation = property(lambda self: self.store.params["color"])
+    alpha_before_activation = property(lambda self: self.store.params["alpha"])
+    svec = property(lambda self: torch.exp(self.store.params["svec"]))
+    color = property(lambda self: torch.sigmoid(self.store.params["color"]))
+    alpha = property(lambda self: torch.sigmoid(self.store.params["alpha"]))
+
+    def train(self, mode: bool = True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    # ---- optimizer -----------------------------------------------------------------------------------------
+    def setup_lr(self, lr_cfg):
+        """cfg.lr (conf/base.yaml:12-26): field -> number | [start, end, steps, type]"""
+        self._lr_cfg = {f: _get(lr_cfg, f) for f in FIELDS}
+        missing = [f for f, v in self._lr_cfg.items() if v is None]
+        if missing:
+            raise RuntimeError(f"no learning rate for {missing}")
+
+    def set_optimizer(self, opt_cfg=None, step: int = 0):
+        """cfg.optimizer (conf/base.yaml:8-11): type Adam, opt_args {eps: 1e-15}"""
+        if self._lr_cfg is None:
+            raise RuntimeError("call setup_lr(cfg.lr) first (trainer.py:162-163)")
+        if _get(opt_cfg, "type", "Adam") != "Adam":
+            raise NotImplementedError("only Adam (the reference's optimizer surgery is Adam-only too, :421-423)")
+        args = _get(opt_cfg, "opt_args", None) or {}
+        self.optimizer = self.store.make_optimizer(self._lr_cfg, max_steps=_get(opt_cfg, "max_steps", 15000),
+                                                   betas=tuple(_get(args, "betas", (0.9, 0.999))),
+                                                   eps=float(_get(args, "eps", 1e-8)))
+        self.optimizer.train_step = step
+        self.store.zero_grad()
+        return self.optimizer
+
+    def update(self, step: int):
+        """update(step) -> update_lr(step) (:451-462): the schedules are evaluated at the trainer's step"""
+        self.step = step
+        if self.optimizer is not None:
+            self.optimizer.train_step = step
+
+    # ---- rendering -----------------------------------------------------------------------------------------
+    def _bg_image(self, camera_info, c2w, use_bg: bool):
+        H, W = camera_info.h, camera_info.w
+        if not use_bg or self.background is None:
+            return None
+        if callable(self.background):
+            return self.background(camera_info.get_rays_d(c2w).to(self.device))
+        return self.background.to(self.device).reshape(1, 1, 3).expand(H, W, 3).contiguous()
+
+    def render_one(self, c2w, camera_info, use_bg: bool = True, rgb_only: bool = False, return_T: bool = False):
+        p = self.store.params
+        out = self._render_fn(
+            p["mean"], p["qvec"], p["svec"], p["alpha"], c2w, camera_info, color=p["color"],
+            bg=self._bg_image(camera_info, c2w, use_bg), rgb_only=rgb_only, raw_params=True,
+            frustum_radius=_get(self.cfg, "frustum_culling_radius", 6.0),
+            tile_radius=_get(self.cfg, "tile_culling_radius", 6.0), T_thresh=_get(self.cfg, "T_thresh", 1e-4),
+            skip_frustum_culling=_get(self.cfg, "skip_frustum_culling", False),
+            depth_detach=_get(self.cfg, "depth_detach", True),
+            grad_sink=self.store.grad_views if self.training else None)
+        aux = out["aux"]
+        if self.training:
+            self._pending.append(aux)  # mask + mean2d gradient are read in post_backward (:1246-1250)
+        res = {"rgb": out["rgb"]}
+        if not rgb_only:  # (the reference's eval-mode `out = out.clamp(0, 1)` at :1405-1406 rebinds a local AFTER
+            # outputs["rgb"] was stored, so the returned image is never clamped -- reproduced by not clamping)
+            res.update(depth=out["depth"], opacity=out["opacity"], z_var=out["z_var"])
+        if return_T:
+            res["T"] = out["T"]
+        return res
+
+    def __call__(self, batch, use_bg: bool = True, rgb_only: bool = False):
+        """forward(batch) (:1426-1460): batch["c2w"] [bs,3,4] (host or device), batch["camera_info"] list"""
+        c2ws, infos = batch["c2w"], batch["camera_info"]
+        return stack_dicts([self.render_one(c2ws[i], infos[i], use_bg, rgb_only) for i in range(len(infos))])
+
+    forward = __call__
+
+    # ---- after the backward pass ---------------------------------------------------------------------------
+    def post_backward(self):
+        """update_densify_info for every view of the step (:464-469, :1471-1476)"""
+        if self.training:
+            for aux in self._pending:
+                self.store.update_densify_info(aux["mask"], aux["mean2d_grad"], aux.get("radii2d"))
+        self._pending = []
+
+    def densify(self, step: int):
+        return self.store.densify_step(step, _get(self.cfg, "densify", {"enabled": False}))
+
+    def prune(self, step: int):
+        return self.store.prune_step(step, _get(self.cfg, "prune", {"enabled": False}))
+
+    # ---- checkpoints ---------------------------------------------------------------------------------------
+    def get_params_for_save(self):
+        return self.store.get_params_for_save()
+
+    @classmethod
+    def load(cls, cfg, ckpt, device="cuda", **kw) -> "GaussianSplattingRenderer":
+        if not isinstance(ckpt, dict):
+            ckpt = torch.load(ckpt, map_location="cpu")
+        if "params" in ckpt:
+            ckpt = ckpt["params"]
+        return cls(cfg, dict({k: ckpt[k] for k in FIELDS}, raw=True), device, **kw)

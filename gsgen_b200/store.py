@@ -99,6 +99,7 @@ class GaussianStore:
             p.requires_grad_(True)
             self.params[name] = p
             self.grad_views[name] = self._rows(self.flat_grad, name, self.N).view(live)
+            p.grad = self.grad_views[name]  # autograd (when no grad_sink is used) accumulates straight into the arena
         if self.optimizer is not None:
             self.optimizer.rebind(self.flat_param, self.flat_grad, self.layout, self.exp_avg, self.exp_avg_sq)
 
