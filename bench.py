@@ -649,6 +649,9 @@ def run_ours(args):
         "ms_per_step_all_runs": all_runs_ms,
         "view_stats": {"N_visible": N_vis, "N_with_dub": D, "D_eff": D_eff, "entries_staged_fwd": staged,
                        "tiles": th * tw},
+        # SURVEY.md §8(d) number (2): tile-list pairs P = sum_tiles (end - start) * 256 = N_with_dub * 256 per view,
+        # identical for the reference and for us when the binning matches (it is bit-exact)
+        "tile_list_pairs_per_s": n_views * D * 256.0 / (ms_max / 1e3),
         "cpu_baseline": cpu_base,
     }
     print(json.dumps(line), flush=True)
