@@ -1,0 +1,347 @@
+// composite_bwd_sh.cu -- per-tile alpha compositing backward for spherical-harmonics payloads of degree >= 1
+// (tile_based_vol_rendering_backward_sh_entry<C>[_bg], vol_render_sh.h:353-455 with the inner loop
+// :268-351 and backward_C :28-36; vol_render_bg.h:131-242).  Round-2 rewrite of the SH specialisation of
+// composite_bwd.cu (which keeps RGB / scalar / SH degree 0).
+//
+// Same per-pair algebra as composite_bwd.cu (one running scalar S per pixel).  What changed, and why (measured on the
+// round-1 kernel, profiles/r1_ncu_full_c3_run10: 734 M warp instructions, 59 % issue slots, top stall = block barrier):
+//   * the per-batch shared accumulator is gone.  Round 1 added every warp's partial sums into a [B x 54] shared array
+//     with float atomics -- CAS loops in SASS (ATOMS.CAST.SPIN), 205 instructions per flush = 19 % of the kernel --
+//     then needed a second block barrier per batch and a per-batch flush of that array.  Now a warp's transpose-buffer
+//     product leaves 4 consecutive coefficients of one (hit, channel) row in each lane and goes straight to HBM/L2 with
+//     ONE red.global.add.v4.f32 per lane (2 per flush), the six geometry sums with one v4 + one v2 reduction per hit.
+//     L2 float atomics are fire-and-forget and aggregate in the 126 MB L2; the (Gaussian, tile) instance is reduced
+//     there instead of in shared memory.
+//   * ONE block barrier per batch (like the forward): it retires the staging buffer and votes on early termination.
+//   * product mapping: lane = (k-quad kq, row group rg); per 4 pixels a lane issues 4 LDS.128 of the basis (rows
+//     4kq..4kq+3) + 2 LDS.128 of the per-pixel factors (rows rg, rg+8) for 16 FFMA2 -- 6 : 16 instead of 7 : 12.
+#include "composite_common.cuh"
+
+namespace gsb {
+
+template <int C> struct ShBwdTraits {
+  static constexpr int CC = C * C;
+  static constexpr int kG = 4;                          // hits per flush
+  static constexpr int kRows = 3 * kG;                  // SH rows of a flush (hit*3 + channel)
+  static constexpr int kKQ = (CC <= 4) ? 1 : 4;         // k-quads (4 coefficients each) spread over the lanes
+  static constexpr int kKL = 4 * kKQ;                   // basis rows held in shared memory (zero beyond CC)
+  static constexpr int kRG = 32 / kKQ;                  // row groups
+  static constexpr int kNR = (kRows + kRG - 1) / kRG;   // rows per lane
+  static constexpr int kTFloats = kG * 9 * 32;          // per warp: [kRows + 6*kG][32 px]
+  static constexpr int kYFloats = kKL * 32;             // per warp: basis [k][32 px]
+  static constexpr int kWarpFloats = kTFloats + kYFloats;
+  static constexpr bool kVec4 = (CC % 4 == 0);          // g_sh rows are 16-byte granular
+};
+
+// physical 16-byte group of logical pixel group q in a transpose-buffer row / basis row (bank-conflict-free reads:
+// the 8 row groups of a product step read rows r, r+1, .. r+7; the 4 k-quads read basis rows 4kq + i)
+__device__ __forceinline__ int t_group(int q, int row) { return (q + row) & 7; }
+__device__ __forceinline__ int y_group(int q, int k) { return (q + 2 * (k >> 2) + (k & 3)) & 7; }
+
+// Flush of a warp's transpose buffer.  SH rows [hit*3+c][32 px] x basis Ysm[k][px] -> g_sh partial sums (vector
+// reduction to global memory); geometry rows -> row sums -> the Gaussian's gradient record (fused) or the
+// reference-layout grad_mean / grad_cov / grad_alpha tensors.
+template <int C, bool FUSED>
+__device__ __noinline__ void flush_direct(const CompositeArgs& a, const float* my_t, const float* my_y,
+                                          const int* ids_stage, int nslot, unsigned slots, int lane) {
+  using ST = ShBwdTraits<C>;
+  constexpr int CC = ST::CC;
+  const int kq = lane & (ST::kKQ - 1);
+  const int rg = lane / ST::kKQ;
+  __syncwarp();
+  float acc[ST::kNR][4], aco[ST::kNR][4];  // even / odd pixel partial sums (FFMA2)
+#pragma unroll
+  for (int i = 0; i < ST::kNR; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; aco[i][j] = 0.f; }
+#pragma unroll 2
+  for (int q = 0; q < 8; ++q) {
+    float4 y4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 4 * kq + j;
+      y4[j] = *reinterpret_cast<const float4*>(my_y + k * 32 + 4 * y_group(q, k));
+    }
+#pragma unroll
+    for (int i = 0; i < ST::kNR; ++i) {
+      const int row = rg + i * ST::kRG;
+      if (ST::kNR * ST::kRG > ST::kRows && row >= ST::kRows) continue;  // (compile-time false when rows tile exactly)
+      const float4 t = *reinterpret_cast<const float4*>(my_t + row * 32 + 4 * t_group(q, row));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ffma2(acc[i][j], aco[i][j], t.x, t.y, y4[j].x, y4[j].y);
+        ffma2(acc[i][j], aco[i][j], t.z, t.w, y4[j].z, y4[j].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ST::kNR; ++i) {
+    const int row = rg + i * ST::kRG;
+    if (row < nslot * 3) {
+      const int h = row / 3, c = row - 3 * h;
+      const int id = ids_stage[(slots >> (8 * h)) & 255u];
+      float* dst = a.grad_pay + (size_t)id * (3 * CC) + c * CC + 4 * kq;
+      const float v0 = acc[i][0] + aco[i][0], v1 = acc[i][1] + aco[i][1];
+      const float v2 = acc[i][2] + aco[i][2], v3 = acc[i][3] + aco[i][3];
+      if (ST::kVec4 && ((reinterpret_cast<uintptr_t>(a.grad_pay) & 15) == 0)) {
+        red_add_v4(dst, v0, v1, v2, v3);
+      } else {
+        if (4 * kq + 0 < CC) red_add(dst + 0, v0);
+        if (4 * kq + 1 < CC) red_add(dst + 1, v1);
+        if (4 * kq + 2 < CC) red_add(dst + 2, v2);
+        if (4 * kq + 3 < CC) red_add(dst + 3, v3);
+      }
+    }
+  }
+  // geometry: row sums, one row per lane (lane = hit*6 + value), then gathered into the hit's first lane
+  float s = 0.f;
+  if (lane < nslot * 6) {
+    const int row = ST::kRows + lane;
+    const float* base = my_t + row * 32;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(base + 4 * t_group(q, row));
+      s += (t.x + t.y) + (t.z + t.w);
+    }
+  }
+  const float s1 = __shfl_down_sync(kFull, s, 1), s2 = __shfl_down_sync(kFull, s, 2);
+  const float s3 = __shfl_down_sync(kFull, s, 3), s4 = __shfl_down_sync(kFull, s, 4);
+  const float s5 = __shfl_down_sync(kFull, s, 5);
+  if (lane < nslot * 6 && (lane % 6) == 0) {
+    const int h = lane / 6;
+    const int id = ids_stage[(slots >> (8 * h)) & 255u];
+    if constexpr (FUSED) {  // {gmx, gmy, gxx, gxy | gyy, galpha, gdepth, -}
+      red_add_v4(a.ggeom + (size_t)id * 8, s, s1, s2, s3);
+      red_add_v2(a.ggeom + (size_t)id * 8 + 4, s4, s5);
+    } else {
+      red_add_v2(a.grad_mean + (size_t)id * 2, s, s1);
+      red_add_v4(a.grad_cov + (size_t)id * 4, s2, s3, s3, s4);
+      red_add(a.grad_alpha + id, s5);
+    }
+  }
+  __syncwarp();
+}
+
+#ifndef GSB_BWDSH_B
+#define GSB_BWDSH_B 32  // list entries per staged batch
+#endif
+#ifndef GSB_BWDSH_MINBLOCKS
+#define GSB_BWDSH_MINBLOCKS 3
+#endif
+
+template <int C, bool FUSED, int B>
+__global__ void __launch_bounds__(kCtaThreads, GSB_BWDSH_MINBLOCKS)
+k_composite_bwd_sh(const CompositeArgs a) {
+  using L = StageLayout<PAY_SH, C, B, true>;
+  using PT = PayTraits<PAY_SH, C>;
+  using ST = ShBwdTraits<C>;
+  constexpr int CC = ST::CC;
+  static_assert(CC >= 4, "SH degree 0 uses the butterfly kernel in composite_bwd.cu");
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t s_bar[2];
+
+  float* s_tbuf = reinterpret_cast<float*>(smem + 2 * L::kBytes);  // [8 warps][kWarpFloats]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile_x = blockIdx.x, tile_y = blockIdx.y;
+  const int tile = tile_y * a.tiles_w + tile_x;
+  const PixelGeom pg = pixel_geom(a, tile_x, tile_y, warp, lane);
+  const int pix = pg.gy * a.W + pg.gx;
+
+  const int s0 = a.start[tile];
+  const int n = (s0 < 0) ? 0 : (a.end[tile] - s0);
+  if (n <= 0) return;
+
+  const bool use_bulk = PT::kBulkOk && ((reinterpret_cast<uintptr_t>(a.sh) & 15) == 0);
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // per-pixel registers
+  float T = 1.0f;
+  bool done = !pg.inside || (1.0f < a.thresh);
+  float go0 = 0.f, go1 = 0.f, go2 = 0.f;
+  float S = 0.f;  // sum_ch go_ch * (F_ch - Cacc_ch)
+  if (pg.inside) {
+    if (a.gout) { go0 = a.gout[3 * pix]; go1 = a.gout[3 * pix + 1]; go2 = a.gout[3 * pix + 2]; }
+    S = go0 * a.fin[3 * pix] + go1 * a.fin[3 * pix + 1] + go2 * a.fin[3 * pix + 2];
+  }
+  float Y[CC];
+  {
+    float c9[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) c9[k] = a.c9_ptr ? a.c9_ptr[k] : a.c9[k];
+    float d[3];
+    pixel_dir(pg.px, pg.py, c9, d);
+    sh_basis<C>(d[0], d[1], d[2], Y);
+  }
+  // per-warp transpose buffer: SH rows [G*3][32] (row = hit*3 + channel), geometry rows [G*6][32], then the block's
+  // basis matrix Ysm[k][32] (k-major); 16-byte groups rotated per row (t_group / y_group)
+  float* my_t = s_tbuf + warp * ST::kWarpFloats;
+  float* my_y = my_t + ST::kTFloats;
+#pragma unroll
+  for (int k = 0; k < ST::kKL; ++k)
+    my_y[k * 32 + 4 * y_group(lane >> 2, k) + (lane & 3)] = (k < CC) ? Y[k < CC ? k : 0] : 0.f;
+  __syncwarp();
+  int nslot = 0;        // hits buffered in my_t (warp-uniform)
+  unsigned slots = 0u;  // their batch entry indices, 8 bits each
+
+  const int nb = (n + B - 1) / B;
+  const int32_t* ids = a.ids + s0;
+  {
+    int cnt0 = min(B, n);
+    int id0 = (tid < cnt0) ? ids[tid] : 0;
+    if (use_bulk && tid == 0) mbar_arrive_expect_tx(&s_bar[0], (uint32_t)cnt0 * 3 * CC * 4);
+    if (tid < B) stage_entry<PAY_SH, C, B, true>(a, smem, tid, id0, tid < cnt0, use_bulk, &s_bar[0]);
+    else cp_async_commit();
+  }
+  int id_next = 0;
+  if (nb > 1) { int j = B + tid; id_next = (tid < B && j < n) ? ids[j] : 0; }
+
+  bool warp_done = __all_sync(kFull, done);
+  cp_async_wait<0>();
+  if (use_bulk) mbar_wait(&s_bar[0], 0u);
+  __syncthreads();
+  // ONE block barrier per batch: batch b+1 is staged before batch b is walked and waited for right before the barrier
+  // that retires batch b's buffer and votes on early termination.
+  for (int b = 0; b < nb; ++b) {
+    unsigned char* st = smem + (b & 1) * L::kBytes;
+    const int cnt = min(B, n - b * B);
+    const bool has_next = (b + 1 < nb);
+    if (has_next) {
+      const int cntn = min(B, n - (b + 1) * B);
+      uint64_t* barn = &s_bar[(b + 1) & 1];
+      if (use_bulk && tid == 0) mbar_arrive_expect_tx(barn, (uint32_t)cntn * 3 * CC * 4);
+      if (tid < B) stage_entry<PAY_SH, C, B, true>(a, smem + ((b + 1) & 1) * L::kBytes, tid, id_next, tid < cntn,
+                                                   use_bulk, barn);
+      else cp_async_commit();
+      if (b + 2 < nb) { int j = (b + 2) * B + tid; id_next = (tid < B && j < n) ? ids[j] : 0; }
+    }
+
+    if (!warp_done) {
+      const float4* sg0 = reinterpret_cast<const float4*>(st + L::kG0);
+      const float4* sg1 = reinterpret_cast<const float4*>(st + L::kG1);
+      const int* sids = reinterpret_cast<const int*>(st + L::kIds);
+      for (int r = 0; r * 32 < cnt; ++r) {
+        const int j = r * 32 + lane;
+        bool hit = false;
+        if (j < cnt) hit = splat_hits_block(sg0[j], sg1[j], pg);
+        unsigned m = __ballot_sync(kFull, hit);
+        // software pipeline over the hits: the next hit's record is fetched while the current one is evaluated
+        int bitn = __ffs(m) - 1;
+        float4 n0 = sg0[m ? r * 32 + bitn : 0], n1 = sg1[m ? r * 32 + bitn : 0];
+        while (m) {
+          const int jj = r * 32 + bitn;
+          const float4 g0 = n0, g1 = n1;
+          m &= m - 1;
+          if (m) { bitn = __ffs(m) - 1; n0 = sg0[r * 32 + bitn]; n1 = sg1[r * 32 + bitn]; }
+          float G, u, v;
+          const float aG = splat_aG(g0, g1, pg.px, pg.py, &G, &u, &v);
+          const bool ok = !done && (aG >= kMinRenderAlpha);
+          if (!__any_sync(kFull, ok)) continue;
+
+          const float w = ok ? aG * T : 0.f;
+          const float* shp = reinterpret_cast<const float*>(st + L::kPay) + jj * (3 * CC);
+          float y[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float s = 0.f;
+            if constexpr (CC % 4 == 0) {
+              const float4* p4 = reinterpret_cast<const float4*>(shp + c * CC);
+              float se = 0.f, so = 0.f;  // even / odd k partial sums: one FFMA2 per coefficient pair
+#pragma unroll
+              for (int k = 0; k < CC / 4; ++k) {
+                float4 q = p4[k];
+                ffma2(se, so, q.x, q.y, Y[4 * k], Y[4 * k + 1]);
+                ffma2(se, so, q.z, q.w, Y[4 * k + 2], Y[4 * k + 3]);
+              }
+              s = se + so;
+            } else {
+#pragma unroll
+              for (int k = 0; k < CC; ++k) s = fmaf(shp[c * CC + k], Y[k], s);
+            }
+            y[c] = sigmoid_fast(s);
+          }
+          const float gc = go0 * y[0] + go1 * y[1] + go2 * y[2];     // sum_ch go_ch * pay_ch
+          const float t0 = w * (y[0] * (1.0f - y[0])) * go0;          // vol_render_sh.h:328-333
+          const float t1 = w * (y[1] * (1.0f - y[1])) * go1;
+          const float t2 = w * (y[2] * (1.0f - y[2])) * go2;
+          // pair gradient (masked by ok through w / okf)
+          const float okf = ok ? 1.0f : 0.f;
+          S = fmaf(-w, gc, S);
+          const float rinv = rcp_approx(1.0f - aG);
+          const float pAG = okf * fmaf(T, gc, -S * rinv);
+          const float gG = pAG * aG;
+          const float vx = kInvCholScale2 * g0.z * u;                        // (S^-1 d).x
+          const float vy = kInvCholScale2 * fmaf(g0.w, u, g1.x * v);         // (S^-1 d).y
+          const float hg = 0.5f * gG;
+          const float e0 = gG * vx, e1 = gG * vy, e2 = hg * vx * vx, e3 = hg * vx * vy, e4 = hg * vy * vy;
+          const float e5 = pAG * G;  // g_alpha (no clamp gate, vol_render.h:409)
+          if (ok) {
+            T = fmaf(-aG, T, T);
+            done = T < a.thresh;
+          }
+          {
+            const int r0 = nslot * 3, g0r = ST::kRows + nslot * 6;
+            const int pg4 = lane >> 2, pe = lane & 3;
+            my_t[(r0 + 0) * 32 + 4 * t_group(pg4, r0 + 0) + pe] = t0;
+            my_t[(r0 + 1) * 32 + 4 * t_group(pg4, r0 + 1) + pe] = t1;
+            my_t[(r0 + 2) * 32 + 4 * t_group(pg4, r0 + 2) + pe] = t2;
+            my_t[(g0r + 0) * 32 + 4 * t_group(pg4, g0r + 0) + pe] = e0;
+            my_t[(g0r + 1) * 32 + 4 * t_group(pg4, g0r + 1) + pe] = e1;
+            my_t[(g0r + 2) * 32 + 4 * t_group(pg4, g0r + 2) + pe] = e2;
+            my_t[(g0r + 3) * 32 + 4 * t_group(pg4, g0r + 3) + pe] = e3;
+            my_t[(g0r + 4) * 32 + 4 * t_group(pg4, g0r + 4) + pe] = e4;
+            my_t[(g0r + 5) * 32 + 4 * t_group(pg4, g0r + 5) + pe] = e5;
+            slots |= (unsigned)jj << (8 * nslot);
+            if (++nslot == ST::kG) {
+              flush_direct<C, FUSED>(a, my_t, my_y, sids, nslot, slots, lane);
+              nslot = 0; slots = 0u;
+            }
+          }
+        }
+        if (__all_sync(kFull, done)) { warp_done = true; break; }
+      }
+      if (nslot) {  // the batch's staging buffer (and its entry indices / ids) is about to be recycled
+        flush_direct<C, FUSED>(a, my_t, my_y, sids, nslot, slots, lane);
+        nslot = 0; slots = 0u;
+      }
+    }
+    if (has_next) {
+      cp_async_wait<0>();
+      if (use_bulk) mbar_wait(&s_bar[(b + 1) & 1], (uint32_t)(((b + 1) >> 1) & 1));
+    }
+    if (__syncthreads_and(warp_done ? 1 : 0)) break;
+  }
+}
+
+template <int C, bool FUSED, int B>
+static int launch_one_sh(const CompositeArgs& a, cudaStream_t st) {
+  using L = StageLayout<PAY_SH, C, B, true>;
+  using ST = ShBwdTraits<C>;
+  static_assert(B <= 256, "entry indices are packed in 8 bits");
+  const size_t smem = 2 * (size_t)L::kBytes + (size_t)8 * ST::kWarpFloats * 4;
+  auto kern = k_composite_bwd_sh<C, FUSED, B>;
+  GSB_CUDA(ensure_max_dyn_smem(reinterpret_cast<const void*>(kern), (int)smem, a.device));
+  dim3 grid(a.tiles_w, a.tiles_h, 1);
+  kern<<<grid, kCtaThreads, smem, st>>>(a);
+  GSB_LAUNCH_CHECK();
+  return GSB200_OK;
+}
+
+int launch_composite_bwd_sh(int C, bool fused, const CompositeArgs& a, cudaStream_t st) {
+  if (a.tiles_w <= 0 || a.tiles_h <= 0) return GSB200_OK;
+  switch (C) {
+    case 2: return fused ? launch_one_sh<2, true, 128>(a, st) : launch_one_sh<2, false, 128>(a, st);
+    case 3: return fused ? launch_one_sh<3, true, GSB_BWDSH_B>(a, st) : launch_one_sh<3, false, GSB_BWDSH_B>(a, st);
+    case 4: return fused ? launch_one_sh<4, true, GSB_BWDSH_B>(a, st) : launch_one_sh<4, false, GSB_BWDSH_B>(a, st);
+    default: break;
+  }
+  set_error("composite_bwd_sh: unsupported C %d", C);
+  return GSB200_ERR_UNSUPPORTED;
+}
+
+}  // namespace gsb

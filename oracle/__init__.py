@@ -333,6 +333,24 @@ def composite_sh_fwd(mean2d, cov2d, sh, alpha, start, end, ids, topleft, c2w9, C
     return (out, T, stats, margin) if want_margin else (out, T, stats)
 
 
+def composite_sh_fwd_exact(mean2d, cov2d, sh, alpha, start, end, ids, topleft, c2w9, C, cfg, bg_rgb=None):
+    """ARBITER, not a restatement: the same composite in fp64 real arithmetic on the fp32 inputs (oracle.c).
+    -> out[H,W,3] f64, T[H,W] f64, margin[H,W] f64."""
+    H, W = cfg["H"], cfg["W"]
+    out = torch.zeros(H, W, 3, dtype=torch.float64)
+    T = torch.ones(H, W, dtype=torch.float64)
+    margin = torch.full((H, W), 1e30, dtype=torch.float64)
+    c_d = ctypes.POINTER(ctypes.c_double)
+    dp = lambda t: ctypes.cast(t.data_ptr(), c_d)
+    c2w9 = c2w9.reshape(-1)[:9].contiguous()
+    lib().orc_composite_sh_fwd_exact(
+        _f(mean2d), _f(cov2d.reshape(-1, 4)), _f(sh.contiguous()), _f(alpha.reshape(-1)), _i(start), _i(end),
+        _i(ids), dp(out), dp(T), _f(topleft), _f(c2w9), cfg["n_tiles_h"], cfg["n_tiles_w"],
+        ctypes.c_float(cfg["psx"]), ctypes.c_float(cfg["psy"]), H, W, C, ctypes.c_float(cfg["thresh"]),
+        _fn(bg_rgb), dp(margin))
+    return out, T, margin
+
+
 def composite_sh_bwd(mean2d, cov2d, sh, alpha, start, end, ids, final, gout, topleft, c2w9, C, cfg):
     N = mean2d.shape[0]
     gm, gc = torch.zeros(N, 2), torch.zeros(N, 4)

@@ -492,6 +492,86 @@ void orc_composite_sh_fwd(const float *mean, const float *cov, const float *sh, 
   if (stats) { stats->pairs_evaluated = pe; stats->pairs_blended = pb; stats->d_eff = de; }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * ARBITER (not a restatement of any reference kernel): the SH composite of A.6 evaluated in REAL
+ * arithmetic -- every operation in fp64 on the fp32 inputs, pixel position = the fp32 value both
+ * implementations use (one rounding of topleft + X*px).  Two correct fp32 implementations differ
+ * from each other by rounding (the reference's fp32 `radial` formula kernels.h:172-193 cancels
+ * catastrophically for thin Gaussians); where they disagree by more than the parity tolerance the
+ * tests ask which of them is within tolerance of this result (tests/test_reference_gpu.py).
+ * margin (nullable) = min over evaluated pairs of |a*G*255 - 1| in fp64.
+ * ---------------------------------------------------------------------------------------- */
+void orc_composite_sh_fwd_exact(const float *mean, const float *cov, const float *sh, const float *alpha,
+                                const int32_t *start, const int32_t *end, const int32_t *ids, double *out,
+                                double *T, const float *topleft, const float *c2w9, int n_tiles_h,
+                                int n_tiles_w, float psx, float psy, int H, int W, int C, float thresh,
+                                const float *bg_rgb, double *margin) {
+  const int CC = C * C;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int tile = 0; tile < n_tiles_h * n_tiles_w; ++tile) {
+    int s = start[tile];
+    int n = (s == -1) ? 0 : end[tile] - s;
+    int ty = tile / n_tiles_w, tx = tile % n_tiles_w;
+    for (int ly = 0; ly < TILE; ++ly)
+      for (int lx = 0; lx < TILE; ++lx) {
+        int gy = ty * TILE + ly, gx = tx * TILE + lx;
+        if (gy >= H || gx >= W) continue;
+        double *o = out + 3 * ((size_t)gy * W + gx);
+        if (n == 0) {
+          for (int c = 0; c < 3; ++c) o[c] = bg_rgb ? (double)bg_rgb[c] : 0.0;
+          if (T) T[(size_t)gy * W + gx] = 1.0;
+          continue;
+        }
+        float posf[2] = {fmaf((float)gx, psx, topleft[0]), fmaf((float)gy, psy, topleft[1])};
+        double px = posf[0], py = posf[1];
+        double d[3], Y[16];
+        for (int r = 0; r < 3; ++r)
+          d[r] = (double)c2w9[3 * r] * px + (double)c2w9[3 * r + 1] * py + (double)c2w9[3 * r + 2];
+        double len = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        double x = d[0] / len, y = d[1] / len, z = d[2] / len;
+        {
+          double xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+          Y[0] = 0.28209479177387814;
+          Y[1] = -0.48860251190291987 * y; Y[2] = 0.48860251190291987 * z; Y[3] = -0.48860251190291987 * x;
+          Y[4] = 1.0925484305920792 * xy; Y[5] = -1.0925484305920792 * yz;
+          Y[6] = 0.94617469575755997 * z2 - 0.31539156525251999; Y[7] = -1.0925484305920792 * xz;
+          Y[8] = 0.54627421529603959 * x2 - 0.54627421529603959 * y2;
+          Y[9] = 0.59004358992664352 * y * (-3.0 * x2 + y2); Y[10] = 2.8906114426405538 * xy * z;
+          Y[11] = 0.45704579946446572 * y * (1.0 - 5.0 * z2); Y[12] = 0.3731763325901154 * z * (5.0 * z2 - 3.0);
+          Y[13] = 0.45704579946446572 * x * (1.0 - 5.0 * z2); Y[14] = 1.4453057213202769 * z * (x2 - y2);
+          Y[15] = 0.59004358992664352 * x * (-x2 + 3.0 * y2);
+        }
+        double acc[3] = {0, 0, 0}, cum = 1.0, mg = 1e30;
+        for (int i = 0; i < n; ++i) {
+          if (cum < (double)thresh) break;
+          int g = ids[s + i];
+          double a = fmin((double)alpha[g], (double)ALPHA_CLAMP);
+          double c0 = cov[4 * g], c1 = cov[4 * g + 1], c2 = cov[4 * g + 2], c3 = cov[4 * g + 3];
+          double det = c0 * c3 - c1 * c2;
+          double dx = px - (double)mean[2 * g], dy = py - (double)mean[2 * g + 1];
+          double radial = ((dx * c3 - dy * c2) * dx + (-dx * c1 + dy * c0) * dy) / det;
+          if (radial < 0.0) radial = 1000.0;
+          double G = exp(-0.5 * radial);
+          double aG = a * G;
+          double m_ = fabs(aG * 255.0 - 1.0);
+          if (m_ < mg) mg = m_;
+          if (aG < (double)MIN_RENDER_ALPHA) continue;
+          double w = aG * cum;
+          for (int c = 0; c < 3; ++c) {
+            double sdot = 0.0;
+            const float *p = sh + (size_t)(3 * g + c) * CC;
+            for (int k = 0; k < CC; ++k) sdot += (double)p[k] * Y[k];
+            acc[c] += w / (1.0 + exp(-sdot));
+          }
+          cum *= (1.0 - aG);
+        }
+        for (int c = 0; c < 3; ++c) o[c] = acc[c] + (bg_rgb ? (double)bg_rgb[c] * cum : 0.0);
+        if (T) T[(size_t)gy * W + gx] = cum;
+        if (margin) margin[(size_t)gy * W + gx] = mg;
+      }
+  }
+}
+
 /* SH composite backward: vol_render_sh.h:353-455 (inner :268-351, backward_C :28-36); with bg:
  * vol_render_bg.h:131-242.  `final` is the saved forward output (incl. bg*T when bg is used). */
 void orc_composite_sh_bwd(int N, const float *mean, const float *cov, const float *sh,

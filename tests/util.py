@@ -82,3 +82,56 @@ def ocam_of(cam):
     import oracle
 
     return oracle.Cam(cam.fx, cam.fy, cam.cx, cam.cy, cam.w, cam.h, cam.near_plane, cam.far_plane)
+
+
+def classify_image_diff(ours, ref, margin_fn, exact_fn=None, atol=IMG_ATOL, what="image", flip_margin=2e-3,
+                        max_flip_frac=2e-3, report=None):
+    """Full-size parity of two fp32 implementations of the same composite (ours vs the reference extension).
+
+    Every pixel with |ours - ref| > atol must be EXPLAINED, by one of
+      (flip)     the pixel sits on the reference's `a*G < 1/255 -> skip` discontinuity: the oracle's margin
+                 min|a*G*255 - 1| over the pixel's evaluated pairs is < flip_margin (error bounded by one blend step);
+      (rounding) the two fp32 results straddle the real-arithmetic value: |ours - exact| <= atol where `exact` is the
+                 fp64 arbiter (oracle.composite_sh_fwd_exact) -- i.e. OURS is within tolerance of the true value and
+                 the remainder is the reference's own fp32 rounding (its `radial` formula, kernels.h:172-193, cancels
+                 for thin Gaussians).
+    margin_fn() -> margin[H,W]; exact_fn() -> (exact[H,W,3] f64, margin_exact[H,W]) are only evaluated when needed.
+    Returns a dict of counts (also appended to `report` when given)."""
+    ours_c, ref_c = ours.detach().float().cpu(), ref.detach().float().cpu()
+    assert ours_c.shape == ref_c.shape, (ours_c.shape, ref_c.shape)
+    assert torch.isfinite(ours_c).all(), f"{what}: non-finite values"
+    err = (ours_c - ref_c).abs()
+    epix = err.amax(dim=-1) if err.dim() == 3 else err
+    bad = epix > atol
+    res = {"what": what, "pixels": int(epix.numel()), "max_abs_diff": float(epix.max()), "over_atol": int(bad.sum()),
+           "atol": atol, "flip_explained": 0, "rounding_explained": 0, "unexplained": 0}
+    if res["over_atol"]:
+        margin = margin_fn().reshape(epix.shape)
+        flip = bad & (margin < flip_margin)
+        rest = bad & ~flip
+        if int(rest.sum()) and exact_fn is not None:
+            exact, margin_x = exact_fn()
+            ex_err = (ours_c.double() - exact.reshape(ours_c.shape)).abs()
+            ex_pix = ex_err.amax(dim=-1) if ex_err.dim() == 3 else ex_err
+            ref_ex = (ref_c.double() - exact.reshape(ours_c.shape)).abs()
+            ref_pix = ref_ex.amax(dim=-1) if ref_ex.dim() == 3 else ref_ex
+            flip_x = rest & (margin_x.reshape(epix.shape) < flip_margin)
+            flip = flip | flip_x
+            rest = rest & ~flip_x
+            rounding = rest & (ex_pix <= atol)
+            res["rounding_explained"] = int(rounding.sum())
+            res["ours_vs_exact_max_at_rounding"] = float(ex_pix[rounding].max()) if int(rounding.sum()) else 0.0
+            res["ref_vs_exact_max_at_rounding"] = float(ref_pix[rounding].max()) if int(rounding.sum()) else 0.0
+            res["ours_vs_exact_max_all"] = float(ex_pix.max())
+            res["ref_vs_exact_max_all"] = float(ref_pix.max())
+            rest = rest & ~rounding
+        res["flip_explained"] = int(flip.sum())
+        res["flip_max_err"] = float(epix[flip].max()) if int(flip.sum()) else 0.0
+        res["unexplained"] = int(rest.sum())
+        res["unexplained_max_err"] = float(epix[rest].max()) if int(rest.sum()) else 0.0
+    if report is not None:
+        report.append(res)
+    assert res["unexplained"] == 0, f"{what}: {res}"
+    assert res.get("flip_max_err", 0.0) <= 8e-3, f"{what}: threshold-flip error larger than one blend step: {res}"
+    assert res["flip_explained"] <= max(4, max_flip_frac * epix.numel()), f"{what}: too many flip pixels: {res}"
+    return res
