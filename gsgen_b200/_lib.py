@@ -20,7 +20,8 @@ c_i32 = ctypes.c_int32
 c_f32 = ctypes.c_float
 c_i64 = ctypes.c_int64
 
-OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_MISMATCH = 0, 1, 2, 3, 4
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_MISMATCH, ERR_OVERFLOW = 0, 1, 2, 3, 4, 5
+OPT_BWD_SH_VARIANT, OPT_ASYNC_COUNT = 1, 2  # GSB200_OPT_* (include/gsb200.h)
 
 
 class Gsb200Camera(ctypes.Structure):
@@ -62,6 +63,7 @@ class Gsb200ViewOut(ctypes.Structure):
         ("rgb", c_void), ("T", c_void), ("depth", c_void), ("opacity", c_void), ("z2", c_void),
         ("mean2d", c_void), ("cov2d", c_void), ("depthg", c_void), ("mask", c_void), ("radii2d", c_void),
         ("h_num_dup", ctypes.POINTER(c_i64)),
+        ("h_generation", ctypes.POINTER(c_i64)),
     ]
 
 
@@ -76,6 +78,7 @@ class Gsb200ViewGrads(ctypes.Structure):
         ("g_mean", c_void), ("g_qvec", c_void), ("g_svec", c_void), ("g_alpha", c_void),
         ("g_color", c_void), ("g_sh", c_void), ("g_mean2d", c_void), ("g_bg", c_void),
         ("accumulate", c_i32),
+        ("generation", c_i64),
     ]
 
 
@@ -92,7 +95,7 @@ EXPORTS = [
     "gsb200_tile_based_vol_rendering_sh", "gsb200_tile_based_vol_rendering_backward_sh",
     "gsb200_project_gaussians_forward", "gsb200_project_gaussians_backward", "gsb200_tile_culling_aabb_count",
     "gsb200_render_forward", "gsb200_render_backward", "gsb200_view_stats",
-    "gsb200_ctx_set_profiling", "gsb200_ctx_get_profile", "gsb200_adam_step",
+    "gsb200_ctx_set_profiling", "gsb200_ctx_get_profile", "gsb200_adam_step", "gsb200_ctx_set_option",
 ]
 
 
@@ -114,10 +117,18 @@ def lib():
     return _lib
 
 
+class TileListOverflow(RuntimeError):
+    """asynchronous-count mode: the view did not fit the tile-list capacity; render it again"""
+
+
 def check(rc: int):
     if rc != OK:
         msg = lib().gsb200_last_error().decode("utf-8", "replace")
-        raise RuntimeError(f"libgsb200 error {rc}: {msg}")
+        raise (TileListOverflow if rc == ERR_OVERFLOW else RuntimeError)(f"libgsb200 error {rc}: {msg}")
+
+
+def set_option(device: torch.device, slot: int, option: int, value: int):
+    check(lib().gsb200_ctx_set_option(ctx(device, slot), ctypes.c_int(option), ctypes.c_int64(value)))
 
 
 def ctx(device: torch.device, slot: int = 0):

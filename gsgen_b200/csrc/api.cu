@@ -2,6 +2,9 @@
 // reference's TORCH_CHECK contracts (gs/src/include/common.h:29-54) but reports through return codes.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
+
+#include <atomic>
 
 #include "kernels.cuh"
 
@@ -96,6 +99,28 @@ static int next_evset(gsb200_ctx::EvSet** sets, int* cap, int* used, gsb200_ctx:
     if (set) GSB_CUDA(cudaEventRecord((set)->e[k], st));     \
   } while (0)
 
+// Asynchronous-count mode: the host consumes the duplicate count of the context's last forward (waits for the 16-byte
+// copy enqueued right behind the front-end kernel -- long done by the time anybody asks).  Returns GSB200_ERR_OVERFLOW
+// when the tile lists did not fit the capacity the sort covered: that view's images / saved state are truncated.
+static int resolve_total(gsb200_ctx* ctx) {
+  if (!ctx->pending_total) return GSB200_OK;
+  int64_t tot[2] = {0, 0};
+  int rc = wait_total(ctx, tot);
+  if (rc) return rc;
+  ctx->pending_total = 0;
+  ctx->D = tot[0];
+  ctx->N_visible = ctx->h_total[1];
+  if (tot[0] > ctx->dup_seen) ctx->dup_seen = tot[0];
+  if (ctx->profiling) ctx->sum_dup += tot[0];
+  GSB_CHECK(tot[0] <= ctx->dup_capacity, GSB200_ERR_OVERFLOW,
+            "asynchronous-count mode: the view expands to %lld duplicates but the tile sort covered %lld (capacity from "
+            "earlier views): its lists are truncated -- render the view again (the capacity has been raised)",
+            (long long)tot[0], (long long)ctx->dup_capacity);
+  return GSB200_OK;
+}
+
+static std::atomic<int64_t> g_generation{0};
+
 }  // namespace gsb
 
 using namespace gsb;
@@ -114,6 +139,9 @@ int gsb200_ctx_create(int device, gsb200_ctx** out) {
   GSB_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   GSB_CUDA(cudaHostAlloc((void**)&c->h_total, 4 * sizeof(int64_t), cudaHostAllocDefault));
+  // tuning / A-B defaults from the environment (the options themselves: gsb200_ctx_set_option)
+  if (const char* e = getenv("GSB200_BWD_SH_VARIANT")) c->bwd_sh_variant = atoi(e);
+  if (const char* e = getenv("GSB200_ASYNC_COUNT")) c->async_count = atoi(e) ? 1 : 0;
   *out = c;
   return GSB200_OK;
 }
@@ -123,7 +151,7 @@ int gsb200_ctx_destroy(gsb200_ctx* c) {
   cudaSetDevice(c->device);
   gsb::Buf* bufs[] = {&c->splat, &c->pay, &c->rect, &c->count, &c->incl, &c->ggeom, &c->gpay, &c->keys[0],
                       &c->keys[1], &c->vals[0], &c->vals[1], &c->cub_tmp, &c->start, &c->end, &c->d_total,
-                      &c->count_sorted, &c->dkeys[0], &c->dkeys[1], &c->perm[0], &c->perm[1], &c->d_stats};
+                      &c->d_overflow, &c->dkeys[0], &c->dkeys[1], &c->perm[0], &c->perm[1], &c->d_stats};
   for (auto* b : bufs) b->release();
   if (c->h_total) cudaFreeHost(c->h_total);
   if (c->ev_total) cudaEventDestroy(c->ev_total);
@@ -145,6 +173,7 @@ int gsb200_tile_culling_aabb_start_end(gsb200_ctx* ctx, const int32_t* tl, const
   int rc;
   if ((rc = set_device(ctx))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->pending_total) { int r2 = resolve_total(ctx); if (r2 && r2 != GSB200_ERR_OVERFLOW) return r2; }
   GSB_CHECK(start && end, GSB200_ERR_INVALID, "tile_culling_aabb_start_end: null start/end");
   GSB_CHECK(tw <= 65535 && th <= 65535, GSB200_ERR_UNSUPPORTED, "tile grid too large");
   if (N > 0) {
@@ -284,6 +313,7 @@ int gsb200_tile_based_vol_rendering_backward_sh(
   a.sh = sh; a.c9_ptr = c2w; a.bg_rgb = bg_rgb;
   a.fin = out; a.gout = grad_out;
   a.grad_mean = grad_mean; a.grad_cov = grad_cov; a.grad_pay = grad_sh; a.grad_alpha = grad_alpha;
+  if (C >= 2 && ctx->bwd_sh_variant == 0) return launch_composite_bwd_sh((int)C, false, a, st);
   return launch_composite_bwd(PAY_SH, (int)C, false, false, a, st);
 }
 
@@ -316,6 +346,7 @@ int gsb200_tile_culling_aabb_count(gsb200_ctx* ctx, const float* mean2d, const f
   if ((rc = set_device(ctx))) return rc;
   GSB_CHECK(tile_size >= 1, GSB200_ERR_INVALID, "tile_size must be positive");
   GSB_CHECK(h_total != nullptr, GSB200_ERR_INVALID, "null h_N_with_dub");
+  if (ctx->pending_total) { int r2 = resolve_total(ctx); if (r2 && r2 != GSB200_ERR_OVERFLOW) return r2; }
   *h_total = 0;
   if (N == 0) return GSB200_OK;
   GSB_CHECK(mean2d && cov2d && tl && br, GSB200_ERR_INVALID, "tile_culling_aabb_count: null tensor");
@@ -353,36 +384,65 @@ int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb
   int64_t D = 0;
   gsb200_ctx::EvSet* ev = nullptr;
   if (ctx->profiling && (rc = next_evset(&ctx->fwd_sets, &ctx->fwd_cap, &ctx->fwd_used, &ev))) return rc;
+  // a count still in flight from the previous forward on this context is consumed first (h_total is reused); an
+  // overflow of THAT view is its own backward's / view_stats' business -- here only the capacity learns from it
+  if (ctx->pending_total) { int rc2 = resolve_total(ctx); if (rc2 && rc2 != GSB200_ERR_OVERFLOW) return rc2; }
+  if (ctx->seen_N != N || ctx->seen_W != cam.W || ctx->seen_H != cam.H) {
+    ctx->seen_N = N; ctx->seen_W = cam.W; ctx->seen_H = cam.H; ctx->dup_seen = 0;
+  }
+  const bool padded = ctx->async_count && ctx->dup_seen > 0 && N > 0;
   GSB_EV(ev, 0, st);
   if (N > 0) {
     GSB_CHECK(in->mean && in->qvec && in->svec && in->alpha, GSB200_ERR_INVALID, "render_forward: null parameter tensor");
+    GSB_CHECK((reinterpret_cast<uintptr_t>(in->qvec) & 15) == 0, GSB200_ERR_INVALID,
+              "render_forward: qvec must be 16-byte aligned (it is read as float4)");
     if ((rc = ctx->splat.reserve((size_t)N * sizeof(Splat)))) return rc;
     if (!is_sh && (rc = ctx->pay.reserve((size_t)N * 16))) return rc;
     if ((rc = ctx->rect.reserve((size_t)N * 8))) return rc;
     if ((rc = ctx->count.reserve((size_t)N * 4))) return rc;
+    if ((rc = reserve_depth_sort(ctx, N))) return rc;
     if ((rc = begin_total(ctx, st))) return rc;
     if ((rc = launch_preprocess(N, in->mean, in->qvec, in->svec, in->alpha, is_sh ? nullptr : in->color, in->act, cam,
                                 out->mean2d, out->cov2d, out->depthg, out->mask, out->radii2d,
                                 ctx->splat.as<Splat>(), ctx->pay.as<float4>(), ctx->rect.as<ushort4>(),
-                                ctx->count.as<int32_t>(), ctx->d_total.as<unsigned long long>(), st)))
+                                ctx->count.as<int32_t>(), ctx->dkeys[0].as<uint32_t>(), ctx->perm[0].as<int32_t>(),
+                                ctx->d_total.as<unsigned long long>(), st)))
       return rc;
     if ((rc = request_total(ctx, st))) return rc;
     GSB_EV(ev, 1, st);
-    if ((rc = sort_depths_and_scan(ctx, N, out->depthg, st))) return rc;  // GPU keeps working ...
-    if ((rc = wait_total(ctx, &D))) return rc;  // ... while the host waits only for the 8-byte count (the one host
-                                                // wait of the view; the reference blocks twice + 5 cudaMalloc/Free)
+    if ((rc = sort_depths_and_scan(ctx, N, out->depthg, st, /*keys_ready=*/true))) return rc;  // GPU keeps working ...
+    if (padded) {
+      // ... and the host does not wait at all: the sort covers a capacity learnt from earlier views of this context
+      // (largest count seen + 1/8), keys beyond the device-side count are padding; the exact count is consumed by
+      // gsb200_render_backward / gsb200_view_stats, which reject the view if it did not fit.
+      ctx->pending_total = 1;
+      ctx->D = -1;
+      ctx->dup_capacity = ctx->dup_seen + ctx->dup_seen / 8 + 4096;
+      D = -1;
+    } else {
+      int64_t tot[2] = {0, 0};
+      if ((rc = wait_total(ctx, tot))) return rc;  // ... while the host waits only for the 16-byte counters (the one
+                                                   // host wait of the view; the reference blocks twice + 5 cudaMalloc/Free)
+      D = tot[0];
+      ctx->N_visible = ctx->h_total[1];
+      ctx->dup_capacity = D;
+      if (D > ctx->dup_seen) ctx->dup_seen = D;
+    }
   } else {
     GSB_EV(ev, 1, st);
+    ctx->N_visible = 0;
   }
   GSB_EV(ev, 2, st);
   if (out->h_num_dup) *out->h_num_dup = D;
-  if ((rc = bin_and_sort(ctx, N, D, cam.tiles_h, cam.tiles_w, nullptr, ctx->start.as<int32_t>(),
-                         ctx->end.as<int32_t>(), st)))
+  if ((rc = bin_and_sort(ctx, N, padded ? ctx->dup_capacity : D, cam.tiles_h, cam.tiles_w, nullptr,
+                         ctx->start.as<int32_t>(), ctx->end.as<int32_t>(), st, padded)))
     return rc;
+  ctx->generation = ++g_generation;
+  if (out->h_generation) *out->h_generation = ctx->generation;
   GSB_EV(ev, 3, st);
   ctx->N = N; ctx->cam = cam; ctx->mode = is_sh ? PAY_SH : PAY_RGB; ctx->C = is_sh ? in->C : 1;
   if (ctx->profiling) {
-    ctx->sum_dup += D;
+    if (D >= 0) ctx->sum_dup += D;  // (asynchronous-count mode: added when the count is consumed)
     if (!ctx->d_stats.p) {
       if ((rc = ctx->d_stats.reserve(16))) return rc;
       GSB_CUDA(cudaMemsetAsync(ctx->d_stats.p, 0, 16, st));
@@ -419,6 +479,13 @@ int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* camin, const gs
   const bool is_sh = in->sh != nullptr;
   GSB_CHECK(ctx->N == in->N && ctx->mode == (is_sh ? PAY_SH : PAY_RGB), GSB200_ERR_INVALID,
             "render_backward: context does not hold the forward state of this view (N=%u vs %u)", ctx->N, in->N);
+  GSB_CHECK(g->generation == 0 || g->generation == ctx->generation, GSB200_ERR_INVALID,
+            "render_backward: the context was overwritten by a later forward (this view is generation %lld, the context "
+            "holds %lld): give every in-flight view its own context",
+            (long long)g->generation, (long long)ctx->generation);
+  if ((rc = resolve_total(ctx))) return rc;  // asynchronous-count mode: rejects a view whose lists were truncated
+  GSB_CHECK(in->N == 0 || ((reinterpret_cast<uintptr_t>(in->qvec) | reinterpret_cast<uintptr_t>(g->g_qvec)) & 15) == 0,
+            GSB200_ERR_INVALID, "render_backward: qvec and g_qvec must be 16-byte aligned (float4 accesses)");
   GSB_CHECK(g->rgb && g->mask && g->g_mean && g->g_qvec && g->g_svec && g->g_alpha, GSB200_ERR_INVALID,
             "render_backward: rgb, mask and g_mean/g_qvec/g_svec/g_alpha are required");
   GSB_CHECK(is_sh ? (g->g_sh != nullptr) : (g->g_color != nullptr), GSB200_ERR_INVALID,
@@ -461,7 +528,11 @@ int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* camin, const gs
   a.grad_pay = g->g_sh;
   a.g_bg = g->g_bg;
   if (ctx->D > 0 || g->g_bg) {
-    if ((rc = launch_composite_bwd(is_sh ? PAY_SH : PAY_RGB, is_sh ? in->C : 1, extras, true, a, st))) return rc;
+    if (is_sh && in->C >= 2 && ctx->bwd_sh_variant == 0) {
+      if ((rc = launch_composite_bwd_sh(in->C, true, a, st))) return rc;
+    } else if ((rc = launch_composite_bwd(is_sh ? PAY_SH : PAY_RGB, is_sh ? in->C : 1, extras, true, a, st))) {
+      return rc;
+    }
   }
   GSB_EV(ev, 1, st);
   rc = launch_project_bwd_fused(N, in->mean, in->qvec, in->svec, in->alpha, is_sh ? nullptr : in->color, in->act,
@@ -554,11 +625,38 @@ int gsb200_view_stats(gsb200_ctx* ctx, int64_t* h_out, gsb200_stream stream) {
   int rc;
   if ((rc = set_device(ctx))) return rc;
   GSB_CHECK(h_out, GSB200_ERR_INVALID, "null h_out");
-  GSB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  GSB_CHECK(ctx->generation != 0, GSB200_ERR_INVALID, "view_stats: no forward has run on this context");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rc_count = resolve_total(ctx);
+  if (rc_count && rc_count != GSB200_ERR_OVERFLOW) return rc_count;
+  const uint32_t T = (uint32_t)ctx->cam.tiles_w * (uint32_t)ctx->cam.tiles_h;
+  if ((rc = ctx->d_overflow.reserve(2 * sizeof(int32_t)))) return rc;
+  int32_t* d_max = ctx->d_overflow.as<int32_t>() + 1;
+  if ((rc = launch_max_list(T, ctx->start.as<int32_t>(), ctx->end.as<int32_t>(), d_max, st))) return rc;
+  int32_t h_max = 0;
+  GSB_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  GSB_CUDA(cudaStreamSynchronize(st));
   h_out[0] = ctx->D;
-  h_out[1] = -1;
-  h_out[2] = -1;
-  return GSB200_OK;
+  h_out[1] = ctx->N_visible;
+  h_out[2] = h_max;
+  return rc_count;  // GSB200_ERR_OVERFLOW: the numbers are valid, the view's lists are not
+}
+
+int gsb200_ctx_set_option(gsb200_ctx* ctx, int option, int64_t value) {
+  GSB_CHECK(ctx != nullptr, GSB200_ERR_INVALID, "null context");
+  switch (option) {
+    case GSB200_OPT_BWD_SH_VARIANT:
+      GSB_CHECK(value == 0 || value == 1, GSB200_ERR_INVALID, "bwd_sh_variant must be 0 or 1");
+      ctx->bwd_sh_variant = (int)value;
+      return GSB200_OK;
+    case GSB200_OPT_ASYNC_COUNT:
+      ctx->async_count = value ? 1 : 0;
+      return GSB200_OK;
+    default:
+      break;
+  }
+  set_error("ctx_set_option: unknown option %d", option);
+  return GSB200_ERR_INVALID;
 }
 
 }  // extern "C"

@@ -462,11 +462,7 @@ static int launch_one(const CompositeArgs& a, cudaStream_t st) {
   using BT = BwdTraits<PAY, C, EXTRAS>;
   const size_t smem = 2 * (size_t)L::kBytes + (size_t)B * BT::kStride * 4 + (size_t)8 * BT::kTbufFloats * 4;
   auto kern = k_composite_bwd<PAY, C, EXTRAS, FUSED, B>;
-  static bool attr_set[64] = {false};
-  if (!attr_set[a.device & 63]) {
-    GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[a.device & 63] = true;
-  }
+  GSB_CUDA(ensure_max_dyn_smem(reinterpret_cast<const void*>(kern), (int)smem, a.device));
   dim3 grid(a.tiles_w, a.tiles_h, 1);
   kern<<<grid, kCtaThreads, smem, st>>>(a);
   GSB_LAUNCH_CHECK();

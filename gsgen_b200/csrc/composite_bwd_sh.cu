@@ -41,8 +41,15 @@ __device__ __forceinline__ int y_group(int q, int k) { return (q + 2 * (k >> 2) 
 // Flush of a warp's transpose buffer.  SH rows [hit*3+c][32 px] x basis Ysm[k][px] -> g_sh partial sums (vector
 // reduction to global memory); geometry rows -> row sums -> the Gaussian's gradient record (fused) or the
 // reference-layout grad_mean / grad_cov / grad_alpha tensors.
+struct FlushDst {  // by value: a reference to the kernel's argument struct would force a local-memory copy of it
+  float* pay;      // g_sh [N,3,C*C]
+  float* g0;       // fused: gradient records [N,8];  else grad_mean [N,2]
+  float* g1;       // else grad_cov [N,4]
+  float* g2;       // else grad_alpha [N]
+};
+
 template <int C, bool FUSED>
-__device__ __noinline__ void flush_direct(const CompositeArgs& a, const float* my_t, const float* my_y,
+__device__ __noinline__ void flush_direct(const FlushDst a, const float* my_t, const float* my_y,
                                           const int* ids_stage, int nslot, unsigned slots, int lane) {
   using ST = ShBwdTraits<C>;
   constexpr int CC = ST::CC;
@@ -80,10 +87,10 @@ __device__ __noinline__ void flush_direct(const CompositeArgs& a, const float* m
     if (row < nslot * 3) {
       const int h = row / 3, c = row - 3 * h;
       const int id = ids_stage[(slots >> (8 * h)) & 255u];
-      float* dst = a.grad_pay + (size_t)id * (3 * CC) + c * CC + 4 * kq;
+      float* dst = a.pay + (size_t)id * (3 * CC) + c * CC + 4 * kq;
       const float v0 = acc[i][0] + aco[i][0], v1 = acc[i][1] + aco[i][1];
       const float v2 = acc[i][2] + aco[i][2], v3 = acc[i][3] + aco[i][3];
-      if (ST::kVec4 && ((reinterpret_cast<uintptr_t>(a.grad_pay) & 15) == 0)) {
+      if (ST::kVec4 && ((reinterpret_cast<uintptr_t>(a.pay) & 15) == 0)) {
         red_add_v4(dst, v0, v1, v2, v3);
       } else {
         if (4 * kq + 0 < CC) red_add(dst + 0, v0);
@@ -111,12 +118,12 @@ __device__ __noinline__ void flush_direct(const CompositeArgs& a, const float* m
     const int h = lane / 6;
     const int id = ids_stage[(slots >> (8 * h)) & 255u];
     if constexpr (FUSED) {  // {gmx, gmy, gxx, gxy | gyy, galpha, gdepth, -}
-      red_add_v4(a.ggeom + (size_t)id * 8, s, s1, s2, s3);
-      red_add_v2(a.ggeom + (size_t)id * 8 + 4, s4, s5);
+      red_add_v4(a.g0 + (size_t)id * 8, s, s1, s2, s3);
+      red_add_v2(a.g0 + (size_t)id * 8 + 4, s4, s5);
     } else {
-      red_add_v2(a.grad_mean + (size_t)id * 2, s, s1);
-      red_add_v4(a.grad_cov + (size_t)id * 4, s2, s3, s3, s4);
-      red_add(a.grad_alpha + id, s5);
+      red_add_v2(a.g0 + (size_t)id * 2, s, s1);
+      red_add_v4(a.g1 + (size_t)id * 4, s2, s3, s3, s4);
+      red_add(a.g2 + id, s5);
     }
   }
   __syncwarp();
@@ -188,6 +195,8 @@ k_composite_bwd_sh(const CompositeArgs a) {
   __syncwarp();
   int nslot = 0;        // hits buffered in my_t (warp-uniform)
   unsigned slots = 0u;  // their batch entry indices, 8 bits each
+  const FlushDst dst = FUSED ? FlushDst{a.grad_pay, a.ggeom, nullptr, nullptr}
+                             : FlushDst{a.grad_pay, a.grad_mean, a.grad_cov, a.grad_alpha};
 
   const int nb = (n + B - 1) / B;
   const int32_t* ids = a.ids + s0;
@@ -298,7 +307,7 @@ k_composite_bwd_sh(const CompositeArgs a) {
             my_t[(g0r + 5) * 32 + 4 * t_group(pg4, g0r + 5) + pe] = e5;
             slots |= (unsigned)jj << (8 * nslot);
             if (++nslot == ST::kG) {
-              flush_direct<C, FUSED>(a, my_t, my_y, sids, nslot, slots, lane);
+              flush_direct<C, FUSED>(dst, my_t, my_y, sids, nslot, slots, lane);
               nslot = 0; slots = 0u;
             }
           }
@@ -306,7 +315,7 @@ k_composite_bwd_sh(const CompositeArgs a) {
         if (__all_sync(kFull, done)) { warp_done = true; break; }
       }
       if (nslot) {  // the batch's staging buffer (and its entry indices / ids) is about to be recycled
-        flush_direct<C, FUSED>(a, my_t, my_y, sids, nslot, slots, lane);
+        flush_direct<C, FUSED>(dst, my_t, my_y, sids, nslot, slots, lane);
         nslot = 0; slots = 0u;
       }
     }

@@ -222,11 +222,7 @@ static int launch_one(const CompositeArgs& a, cudaStream_t st) {
   using L = StageLayout<PAY, C, B, false>;
   const size_t smem = 2 * (size_t)L::kBytes;
   auto kern = k_composite_fwd<PAY, C, EXTRAS, B>;
-  static bool attr_set[64] = {false};  // per instantiation and device
-  if (!attr_set[a.device & 63]) {
-    GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[a.device & 63] = true;
-  }
+  GSB_CUDA(ensure_max_dyn_smem(reinterpret_cast<const void*>(kern), (int)smem, a.device));
   dim3 grid(a.tiles_w, a.tiles_h, 1);
   kern<<<grid, kCtaThreads, smem, st>>>(a);
   GSB_LAUNCH_CHECK();

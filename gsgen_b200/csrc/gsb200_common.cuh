@@ -65,7 +65,6 @@ struct gsb200_ctx {
   gsb::Buf rect;      // ushort4[N]           8 B  tile rectangle
   gsb::Buf count;     // int32[N]
   gsb::Buf incl;      // int32[N]            inclusive scan of count (in depth order)
-  gsb::Buf count_sorted;  // int32[N]        count gathered in depth order
   gsb::Buf dkeys[2];  // uint32[N]           depth bits (radix sort double buffer)
   gsb::Buf perm[2];   // int32[N]            Gaussian indices in depth order
   gsb::Buf ggeom;     // float[N*8]          gradient record (gmx,gmy,gxx,gxy | gyy,galpha,gdepth,-)
@@ -77,12 +76,22 @@ struct gsb200_ctx {
   // per-tile
   gsb::Buf start, end;  // int32[T]
   // host-visible scalars
-  int64_t* h_total = nullptr;  // pinned
-  gsb::Buf d_total;            // unsigned long long[1] device-side duplicate counter
+  int64_t* h_total = nullptr;  // pinned [4]: duplicates, visible Gaussians, overflow flag, max list length
+  gsb::Buf d_total;            // unsigned long long[2] device-side counters (duplicates, visible Gaussians)
+  gsb::Buf d_overflow;         // int32[2]: [0] tile-list capacity overflow flag (async-count mode), [1] max list length
   cudaEvent_t ev_total = nullptr;
+  // options (gsb200_ctx_set_option)
+  int bwd_sh_variant = 0;      // 0: direct vector-reduction flush (composite_bwd_sh.cu); 1: round-1 shared accumulator
+  int async_count = 0;         // 1: render_forward does not wait for N_with_dub (capacity from earlier views)
   // saved view state
   uint32_t N = 0;
-  int64_t D = 0;
+  int64_t D = 0;               // exact duplicate count of the last view, -1 while unresolved (async-count mode)
+  int64_t dup_capacity = 0;    // async-count mode: entries the tile sort covered (>= D unless overflow)
+  int64_t dup_seen = 0;        // largest N_with_dub this context has seen for the current (N, image size)
+  uint32_t seen_N = 0; int seen_W = 0, seen_H = 0;
+  int pending_total = 0;       // 1: an asynchronous count is in flight (ev_total / h_total not consumed yet)
+  int64_t generation = 0;      // stamp of the forward whose state the context holds (0 = none)
+  int64_t N_visible = -1;
   int sorted_sel = 0;          // which vals[] holds the sorted ids
   gsb::Camera cam;
   int mode = 0, C = 0;

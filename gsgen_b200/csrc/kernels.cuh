@@ -71,7 +71,7 @@ int launch_pack_splats(uint32_t N, const float* mean2d, const float* cov2d, cons
 int launch_preprocess(uint32_t N, const float* mean, const float* qvec, const float* svec, const float* alpha,
                       const float* color, int act, const Camera& cam, float* mean2d, float* cov2d, float* depthg,
                       uint8_t* mask, float* radii2d, Splat* splat, float4* pay, ushort4* rect, int32_t* count,
-                      unsigned long long* total, cudaStream_t st);
+                      uint32_t* dkeys, int32_t* perm0, unsigned long long* total, cudaStream_t st);
 int launch_project_bwd_fused(uint32_t N, const float* mean, const float* qvec, const float* svec,
                              const float* alpha, const float* color, int act, const uint8_t* mask, const Camera& cam, const float4* ggeom, const float4* gpay,
                              float* g_mean, float* g_qvec, float* g_svec, float* g_alpha, float* g_color,
@@ -90,12 +90,24 @@ int launch_adam_flat(float* param, const float* grad, float* exp_avg, float* exp
 int begin_total(gsb200_ctx* ctx, cudaStream_t st);    // zero the device-side duplicate counter
 int request_total(gsb200_ctx* ctx, cudaStream_t st);  // async D2H copy + event
 int wait_total(gsb200_ctx* ctx, int64_t* h_total);    // host waits for that event only
-int sort_depths_and_scan(gsb200_ctx* ctx, uint32_t N, const float* depth, cudaStream_t st);
+int reserve_depth_sort(gsb200_ctx* ctx, uint32_t N);   // dkeys / perm / incl for N Gaussians
+int sort_depths_and_scan(gsb200_ctx* ctx, uint32_t N, const float* depth, cudaStream_t st, bool keys_ready = false);
 int bin_and_sort(gsb200_ctx* ctx, uint32_t N, int64_t D, int tiles_h, int tiles_w, int32_t* ids_out, int32_t* start,
-                 int32_t* end, cudaStream_t st);
+                 int32_t* end, cudaStream_t st, bool padded = false);
+int launch_max_list(uint32_t T, const int32_t* start, const int32_t* end, int32_t* out, cudaStream_t st);
 
 // composite_fwd.cu / composite_bwd.cu
 int launch_composite_fwd(int pay_kind, int C, bool extras, const CompositeArgs& a, cudaStream_t st);
 int launch_composite_bwd(int pay_kind, int C, bool extras, bool fused, const CompositeArgs& a, cudaStream_t st);
+// composite_bwd_sh.cu (round 2): SH degree >= 1 with the direct vector-reduction flush
+int launch_composite_bwd_sh(int C, bool fused, const CompositeArgs& a, cudaStream_t st);
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  Called before every launch: the attribute is per
+// (function, device) and the call is a few hundred ns -- cheaper than a lock-protected per-device cache, and correct
+// when several host threads drive different devices through the same library (round-1 advice: the lazy
+// `static bool attr_set[64]` was an unsynchronised init).
+inline cudaError_t ensure_max_dyn_smem(const void* func, int bytes, int /*device*/) {
+  return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
 
 }  // namespace gsb

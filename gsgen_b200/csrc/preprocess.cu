@@ -12,18 +12,20 @@ namespace gsb {
 
 constexpr int kThreads = 256;
 
-// adds the block's sum of per-thread duplicate counts into *total (one 64-bit atomic per block); must be reached
-// by every thread of the block
-__device__ __forceinline__ void block_add_total(int v, unsigned long long* total) {
-  __shared__ int s_part[kThreads / 32];
+// adds the block's sum of per-thread duplicate counts into total[0] (and, when vis >= 0, the number of Gaussians that
+// passed the frustum test into total[1]): one 64-bit atomic per block and counter; must be reached by every thread
+__device__ __forceinline__ void block_add_total(int v, unsigned long long* total, int vis = -1) {
+  __shared__ int s_part[2][kThreads / 32];
   v = __reduce_add_sync(0xffffffffu, v);
-  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+  const int nv = (vis >= 0) ? __reduce_add_sync(0xffffffffu, vis) : 0;
+  if ((threadIdx.x & 31) == 0) { s_part[0][threadIdx.x >> 5] = v; s_part[1][threadIdx.x >> 5] = nv; }
   __syncthreads();
   if (threadIdx.x == 0 && total) {
-    int t = 0;
+    int t = 0, u = 0;
 #pragma unroll
-    for (int i = 0; i < kThreads / 32; ++i) t += s_part[i];
+    for (int i = 0; i < kThreads / 32; ++i) { t += s_part[0][i]; u += s_part[1][i]; }
     if (t) atomicAdd(total, (unsigned long long)t);
+    if (vis >= 0 && u) atomicAdd(total + 1, (unsigned long long)u);
   }
 }
 
@@ -150,8 +152,9 @@ __device__ __forceinline__ int preprocess_one(
     const float* __restrict__ alpha, const float* __restrict__ color, int act, const Camera& cam,
     float* __restrict__ mean2d, float* __restrict__ cov2d, float* __restrict__ depthg, uint8_t* __restrict__ mask,
     float* __restrict__ radii2d, Splat* __restrict__ splat, float4* __restrict__ pay, ushort4* __restrict__ rect,
-    int32_t* __restrict__ count) {
+    int32_t* __restrict__ count, uint32_t* __restrict__ dkeys, int32_t* __restrict__ perm0, bool* vis) {
   float x[3] = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2]};
+  perm0[i] = (int32_t)i;  // input of the per-Gaussian depth sort (binning.cu step 1), written here: one launch less
   // raw leaves -> activated values in registers; act == 0: the tensors are already activated
   float s[3] = {act_svec(svec[3 * i], act), act_svec(svec[3 * i + 1], act), act_svec(svec[3 * i + 2], act)};
   bool keep = true;
@@ -160,10 +163,12 @@ __device__ __forceinline__ int preprocess_one(
     keep = sphere_in_frustum(x, r, cam.fn, cam.fp);
   }
   mask[i] = keep ? 1 : 0;
+  *vis = keep;
   if (!keep) {
     reinterpret_cast<float2*>(mean2d)[i] = make_float2(0.f, 0.f);
     reinterpret_cast<float4*>(cov2d)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     depthg[i] = 0.f;
+    dkeys[i] = 0u;
     if (radii2d) radii2d[i] = 0.f;
     count[i] = 0;
     return 0;
@@ -175,6 +180,7 @@ __device__ __forceinline__ int preprocess_one(
   reinterpret_cast<float2*>(mean2d)[i] = make_float2(f.mean2d[0], f.mean2d[1]);
   reinterpret_cast<float4*>(cov2d)[i] = make_float4(f.cov[0], f.cov[1], f.cov[2], f.cov[3]);
   depthg[i] = f.depth;
+  dkeys[i] = __float_as_uint(f.depth);
   if (radii2d) radii2d[i] = radius2d(f.cov);
   Splat sp = make_splat(f.mean2d, f.cov, act_alpha(alpha[i], act));
   int r[4];
@@ -200,12 +206,13 @@ k_preprocess(uint32_t N, const float* __restrict__ mean, const float* __restrict
              int act, Camera cam, float* __restrict__ mean2d, float* __restrict__ cov2d, float* __restrict__ depthg,
              uint8_t* __restrict__ mask, float* __restrict__ radii2d, Splat* __restrict__ splat,
              float4* __restrict__ pay, ushort4* __restrict__ rect, int32_t* __restrict__ count,
-             unsigned long long* __restrict__ total) {
+             uint32_t* __restrict__ dkeys, int32_t* __restrict__ perm0, unsigned long long* __restrict__ total) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  block_add_total(i < N ? preprocess_one(i, mean, qvec, svec, alpha, color, act, cam, mean2d, cov2d, depthg, mask, radii2d,
-                                         splat, pay, rect, count)
-                        : 0,
-                  total);
+  bool vis = false;
+  const int cnt = i < N ? preprocess_one(i, mean, qvec, svec, alpha, color, act, cam, mean2d, cov2d, depthg, mask,
+                                         radii2d, splat, pay, rect, count, dkeys, perm0, &vis)
+                        : 0;
+  block_add_total(cnt, total, vis ? 1 : 0);
 }
 
 
@@ -323,10 +330,10 @@ int launch_pack_splats(uint32_t N, const float* mean2d, const float* cov2d, cons
 int launch_preprocess(uint32_t N, const float* mean, const float* qvec, const float* svec, const float* alpha,
                       const float* color, int act, const Camera& cam, float* mean2d, float* cov2d, float* depthg,
                       uint8_t* mask, float* radii2d, Splat* splat, float4* pay, ushort4* rect, int32_t* count,
-                      unsigned long long* total, cudaStream_t st) {
+                      uint32_t* dkeys, int32_t* perm0, unsigned long long* total, cudaStream_t st) {
   if (N == 0) return GSB200_OK;
   k_preprocess<<<grid1d(N), kThreads, 0, st>>>(N, mean, qvec, svec, alpha, color, act, cam, mean2d, cov2d, depthg, mask,
-                                              radii2d, splat, pay, rect, count, total);
+                                              radii2d, splat, pay, rect, count, dkeys, perm0, total);
   GSB_LAUNCH_CHECK();
   return GSB200_OK;
 }

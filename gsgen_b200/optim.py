@@ -103,8 +103,14 @@ class FlatAdam:
             if name not in self.schedulers:
                 raise RuntimeError(f"no learning rate for field '{name}'")
         self._fields = (Gsb200AdamField * len(self.layout))()
+        total = flat_param.numel()
         for i, (_, _, off, n) in enumerate(self.layout):
-            self._fields[i].begin, self._fields[i].count = off, n
+            # the C ABI wants fields that tile [0, total): a field's count runs up to the next field's (16-byte aligned)
+            # offset, i.e. includes the alignment padding -- zero gradient and zero moments there, so nothing moves
+            nxt = self.layout[i + 1][2] if i + 1 < len(self.layout) else total
+            if nxt < off + n:
+                raise RuntimeError("layout fields overlap or exceed the buffer")
+            self._fields[i].begin, self._fields[i].count = off, nxt - off
 
     def lr_at(self, step: int) -> Dict[str, float]:
         """what update_lr(step) writes into the param groups (gs/gaussian_splatting.py:451-454)"""

@@ -21,7 +21,10 @@ FIELDS_RGB = (("mean", 3), ("qvec", 4), ("svec", 3), ("alpha", 1), ("color", 3))
 
 
 def field_layout(N: int, C: Optional[int]) -> List[tuple]:
-    """[(name, shape, offset, numel)] of the flat buffers.  C=None -> RGB colour, else SH [N,3,C*C]."""
+    """[(name, shape, offset, numel)] of the flat buffers.  C=None -> RGB colour, else SH [N,3,C*C].
+    Every field starts on a 16-byte boundary (offset % 4 == 0): the kernels read qvec / write g_qvec as float4 and
+    stream the buffers 16 bytes at a time, so a field must not start mid-vector when N % 4 != 0.  The (at most 3)
+    padding floats between fields belong to no Gaussian: zero gradient, zero moments, never read."""
     fields = [("mean", (N, 3)), ("qvec", (N, 4)), ("svec", (N, 3)), ("alpha", (N,))]
     fields.append(("color", (N, 3)) if C is None else ("sh", (N, 3, C * C)))
     out, off = [], 0
@@ -30,8 +33,14 @@ def field_layout(N: int, C: Optional[int]) -> List[tuple]:
         for s in shape:
             n *= s
         out.append((name, shape, off, n))
-        off += n
+        off = (off + n + 3) // 4 * 4
     return out
+
+
+def layout_total(layout) -> int:
+    """floats of a flat buffer with this layout (fields + alignment padding, a multiple of 4)"""
+    _, _, off, n = layout[-1]
+    return (off + n + 3) // 4 * 4
 
 
 def shard_views(n_views: int, rank: int, world: int) -> List[int]:
@@ -47,16 +56,22 @@ class ViewParallelRenderer:
     host-side logic (layout, sharding, collective) is testable on CPU with gloo.
     """
 
-    def __init__(self, params: Dict[str, torch.Tensor], C: Optional[int], device, group=None):
+    def __init__(self, params: Dict[str, torch.Tensor], C: Optional[int], device, group=None,
+                 register_nccl: bool = False):
         self.C = C
         self.device = torch.device(device)
         self.group = group
         N = params["mean"].shape[0]
         self.N = N
         self.layout = field_layout(N, C)
-        total = self.layout[-1][2] + self.layout[-1][3]
-        self.flat_param = torch.empty(total, dtype=torch.float32, device=self.device)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        total = layout_total(self.layout)
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.grad_buffer_kind = "plain"
+        self.flat_grad = None
+        if register_nccl and self.world > 1 and self.device.type == "cuda":
+            self.flat_grad = self._alloc_registered(total)
+        if self.flat_grad is None:
+            self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
         self.params: Dict[str, torch.Tensor] = {}
         self.grad_views: Dict[str, torch.Tensor] = {}
         for name, shape, off, n in self.layout:
@@ -65,6 +80,25 @@ class ViewParallelRenderer:
             p.requires_grad_(True)
             self.params[name] = p
             self.grad_views[name] = self.flat_grad[off:off + n].view(shape)
+
+    def _alloc_registered(self, total: int):
+        """The all-reduce operand allocated with ncclMemAlloc and registered with the communicator (NCCL user-buffer
+        registration): on an NVSwitch box NCCL can then run the 118-236 MB gradient all-reduce through NVLS
+        (in-switch reduction, zero-copy) instead of staging it through its own buffers.  Returns None when this torch /
+        NCCL build does not offer the allocator -- the caller falls back to a plain tensor (`grad_buffer_kind`)."""
+        try:
+            pg = self.group if self.group is not None else dist.group.WORLD
+            backend = pg._get_backend(self.device)
+            pool = torch.cuda.MemPool(backend.mem_allocator)
+            with torch.cuda.use_mem_pool(pool):
+                buf = torch.zeros(total, dtype=torch.float32, device=self.device)
+            backend.register_mem_pool(pool)
+            self._nccl_pool = pool  # keeps the registration alive
+            self.grad_buffer_kind = "ncclMemAlloc + register_mem_pool"
+            return buf
+        except Exception as ex:  # pragma: no cover (needs NCCL)
+            self.grad_buffer_kind = f"plain (registration unavailable: {type(ex).__name__}: {str(ex)[:80]})"
+            return None
 
     @property
     def world(self) -> int:

@@ -89,20 +89,24 @@ class _RenderView(torch.autograd.Function):
         mask = torch.empty(N, device=dev, dtype=torch.bool)
         radii = torch.empty(N, **f32)
         ndup = ctypes.c_int64(0)
+        gen = ctypes.c_int64(0)
         vout = Gsb200ViewOut()
         vout.rgb, vout.T = fptr(rgb), fptr(T)
         vout.depth, vout.opacity, vout.z2 = fptr(depth), fptr(opacity), fptr(z2)
         vout.mean2d, vout.cov2d, vout.depthg = fptr(mean2d), fptr(cov2d), fptr(depthg)
         vout.mask, vout.radii2d = ptr(mask, torch.bool), fptr(radii)
         vout.h_num_dup = ctypes.pointer(ndup)
+        vout.h_generation = ctypes.pointer(gen)
         c = _lib.ctx(dev, slot)
         _lib.check(_lib.lib().gsb200_render_forward(c, ctypes.byref(cam), ctypes.byref(vin), ctypes.byref(vout),
                                                     _lib.stream_ptr(dev)))
         ctx.save_for_backward(mean, qvec, svec, alpha, color, sh, bg, bg_rgb, rgb, depth, opacity, z2, T, mask)
         ctx.cam, ctx.C, ctx.sh_c2w9, ctx.slot, ctx.extras, ctx.aux = cam, C, sh_c2w9, slot, extras, aux
         ctx.grad_sink, ctx.act = grad_sink, int(act)
-        if aux is not None:
-            aux.update(mask=mask, cov2d=cov2d, depth=depthg, radii2d=radii, N_with_dub=int(ndup.value))
+        ctx.generation = int(gen.value)  # the context holds THIS view until another forward runs on the same slot
+        if aux is not None:  # N_with_dub is None in asynchronous-count mode (view_stats() reads it later)
+            aux.update(mask=mask, cov2d=cov2d, depth=depthg, radii2d=radii,
+                       N_with_dub=int(ndup.value) if ndup.value >= 0 else None, slot=slot)
         ctx.mark_non_differentiable(T)
         ctx.set_materialize_grads(False)  # unused outputs arrive as None instead of freshly zero-filled tensors
         zero = None
@@ -153,6 +157,7 @@ class _RenderView(torch.autograd.Function):
         gbg = torch.empty_like(bg) if need_bg else None
         g.g_mean, g.g_qvec, g.g_svec, g.g_alpha = fptr(gm), fptr(gq), fptr(gs), fptr(ga)
         g.g_color, g.g_sh, g.g_mean2d, g.g_bg = fptr(gcol), fptr(gsh), fptr(gm2), fptr(gbg)
+        g.generation = ctx.generation  # fails loudly if a later forward re-used this view's context slot
         c = _lib.ctx(dev, ctx.slot)
         _lib.check(_lib.lib().gsb200_render_backward(c, ctypes.byref(cam), ctypes.byref(vin), ctypes.byref(g),
                                                      _lib.stream_ptr(dev)))
@@ -166,7 +171,7 @@ class _RenderView(torch.autograd.Function):
 def render_view(mean, qvec, svec, alpha, c2w, camera_info, *, color=None, sh=None, C: int = 1, bg=None, bg_rgb=None,
                 rgb_only: bool = False, sh_c2w=None, frustum_radius=6.0, tile_radius=6.0, T_thresh=1e-4,
                 skip_frustum_culling=False, depth_detach=True, slot: int = 0, grad_sink=None,
-                raw_params: bool = False):
+                raw_params: bool = False, async_count: bool = False):
     """One view through the fused path.  Returns the dict `render_one` returns
     ({"rgb","depth","opacity","z_var"} (+"T")) plus "aux" (mask, mean2d, cov2d, depth, radii2d, N_with_dub).
 
@@ -177,6 +182,14 @@ def render_view(mean, qvec, svec, alpha, c2w, camera_info, *, color=None, sh=Non
     raw_params: svec / alpha / color are the raw leaves (`*_before_activation`); exp / sigmoid / sigmoid run inside the
                 kernels and the returned (or sunk) gradients are w.r.t. the raw leaves.  SH coefficients have no
                 activation in the reference (sh_renderer.py:38-43), so only svec / alpha are affected on the SH path.
+
+    slot:       index of the library context (scratch arena + the view's saved binning / splat records) to use.  A
+                context holds ONE view between its forward and its backward: every view that is in flight at the same
+                time (a batch rendered before one loss.backward()) needs its own slot; the backward raises if its slot
+                was overwritten.
+    async_count: no host wait in the forward (GSB200_OPT_ASYNC_COUNT, include/gsb200.h): the tile sort covers a capacity
+                learnt from the slot's earlier views; aux["N_with_dub"] is None; the backward (or `view_stats`) raises
+                `_lib.TileListOverflow` if the view did not fit -- render it again.
 
     color given -> RGB path (render_with_T + 3x render_scalar semantics, per-pixel bg[H,W,3]);
     sh given    -> SH path  (render_sh / render_sh_bg semantics, constant bg_rgb[3]); `sh_c2w` is the tensor the
@@ -192,6 +205,7 @@ def render_view(mean, qvec, svec, alpha, c2w, camera_info, *, color=None, sh=Non
         src = c2w if sh_c2w is None else sh_c2w
         sh_c2w9 = src.detach().to("cpu", torch.float32).contiguous().view(-1)[:9].tolist()
     aux = {}
+    _lib.set_option(mean.device, slot, _lib.OPT_ASYNC_COUNT, 1 if async_count else 0)
     act = 0
     if raw_params:
         act = _lib.ACT_SVEC_EXP | _lib.ACT_ALPHA_SIGMOID | (_lib.ACT_COLOR_SIGMOID if sh is None else 0)
@@ -204,3 +218,11 @@ def render_view(mean, qvec, svec, alpha, c2w, camera_info, *, color=None, sh=Non
     aux["mean2d"] = mean2d
     out["aux"] = aux
     return out
+
+
+def view_stats(device, slot: int = 0):
+    """(N_with_dub, N_visible, longest tile list) of the last forward on the slot's context (synchronises)."""
+    h = (ctypes.c_int64 * 3)()
+    dev = torch.device(device)
+    _lib.check(_lib.lib().gsb200_view_stats(_lib.ctx(dev, slot), h, _lib.stream_ptr(dev)))
+    return int(h[0]), int(h[1]), int(h[2])

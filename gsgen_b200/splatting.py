@@ -146,7 +146,10 @@ class GaussianSplattingRenderer:
             tile_radius=_get(self.cfg, "tile_culling_radius", 6.0), T_thresh=_get(self.cfg, "T_thresh", 1e-4),
             skip_frustum_culling=_get(self.cfg, "skip_frustum_culling", False),
             depth_detach=_get(self.cfg, "depth_detach", True),
-            grad_sink=self.store.grad_views if self.training else None)
+            grad_sink=self.store.grad_views if self.training else None,
+            # one library context per in-flight view: the views of a batch are all rendered before ONE loss.backward()
+            # (trainer.py:575-599), and a context keeps a view's binning + splat records until its backward has run
+            slot=len(self._pending) if self.training else 0)
         aux = out["aux"]
         if self.training:
             self._pending.append(aux)  # mask + mean2d gradient are read in post_backward (:1246-1250)
@@ -181,7 +184,18 @@ class GaussianSplattingRenderer:
 
     # ---- checkpoints ---------------------------------------------------------------------------------------
     def get_params_for_save(self):
-        return self.store.get_params_for_save()
+        """gs/gaussian_splatting.py:294-303: the raw leaves + `cfg` + `bg` (the reference's `load` does
+        OmegaConf.create(ckpt["cfg"]) and utils/export.to_ply / to_splat read ckpt["cfg"]["prompt"]).  Optimizer state is
+        not part of a renderer checkpoint in the reference either."""
+        params = self.store.get_params_for_save()
+        cfg = self.cfg
+        if hasattr(cfg, "items"):  # a plain container (OmegaConf.to_container in the reference)
+            cfg = {k: (dict(v) if hasattr(v, "items") else v) for k, v in cfg.items()}
+        params["cfg"] = cfg if cfg is not None else {}
+        bg = self.background
+        params["bg"] = bg.state_dict() if hasattr(bg, "state_dict") else ({} if bg is None or callable(bg)
+                                                                           else {"color": torch.as_tensor(bg).cpu()})
+        return params
 
     @classmethod
     def load(cls, cfg, ckpt, device="cuda", **kw) -> "GaussianSplattingRenderer":

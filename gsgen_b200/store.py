@@ -32,7 +32,7 @@ from typing import Dict, Optional
 import torch
 import torch.distributed as dist
 
-from .parallel import field_layout
+from .parallel import field_layout, layout_total
 
 
 def quat_to_rotmat(q: torch.Tensor) -> torch.Tensor:
@@ -61,7 +61,7 @@ class GaussianStore:
         self.C, self.group, self.growth = C, group, float(growth)
         self.device = torch.device(device) if device is not None else params["mean"].device
         self.N = int(params["mean"].shape[0])
-        self.cap = max(int(capacity or 0), self.N, 1)
+        self.cap = self._round_cap(max(int(capacity or 0), self.N, 1))
         self.optimizer = None
         self._alloc(self.cap)
         for name, shape, off, n in field_layout(self.N, C):
@@ -71,10 +71,17 @@ class GaussianStore:
         self._make_leaves()
 
     # ---- arena ---------------------------------------------------------------------------------------
+    @staticmethod
+    def _round_cap(cap: int) -> int:
+        """capacities are multiples of 4 rows: every field of every buffer then starts on a 16-byte boundary (the
+        kernels access qvec / g_qvec as float4; a capacity like 6145 = int(4096*1.5)+1 used to misalign them)"""
+        return (int(cap) + 3) // 4 * 4
+
     def _alloc(self, cap: int):
+        cap = self._round_cap(cap)
         self.cap = cap
         self.layout = field_layout(cap, self.C)
-        total = self.layout[-1][2] + self.layout[-1][3]
+        total = layout_total(self.layout)
         mk = lambda: torch.zeros(total, dtype=torch.float32, device=self.device)
         self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq = mk(), mk(), mk(), mk()
         self._field = {name: (shape, off) for name, shape, off, _ in self.layout}
@@ -139,16 +146,42 @@ class GaussianStore:
     def grad_bytes(self) -> int:
         return sum(v.numel() for v in self.grad_views.values()) * 4
 
+    def world_size(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
     def all_reduce(self):
         """SUM over ranks of the live gradient rows (one flat collective when the arena is full, else one per
         field -- dead capacity is not sent)."""
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+        if self.world_size() == 1:
             return
         if self.N == self.cap:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
         else:
             for name in self._field:
                 dist.all_reduce(self._rows(self.flat_grad, name, self.N), op=dist.ReduceOp.SUM, group=self.group)
+
+    def sync_densify_info(self):
+        """Replica consistency of the view-parallel mode.  The densification statistics are
+        per-view side effects (`mean_2d_grad_accum += |g_mean2d|`, `cnt += 1` under each view's mask,
+        gs/gaussian_splatting.py:464-469; `max_radii2d = max(...)`, :1240-1245); with the views of a batch sharded over
+        ranks every rank only holds its own views' share.  Called before anything reads them (`densify_step` /
+        `prune_step`): SUM of the LOCAL contributions since the last synchronisation for the two accumulators (one
+        [2,N] collective), MAX for the radii -- after which all ranks hold exactly the numbers a single process
+        rendering all views would, and select the same Gaussians."""
+        if self.world_size() == 1:
+            return
+        if self._acc_base is None or self._acc_base.shape[1] != self.N:
+            raise RuntimeError("densification statistics changed length outside densify / prune")
+        local = torch.stack((self.mean_2d_grad_accum, self.cnt)) - self._acc_base
+        dist.all_reduce(local, op=dist.ReduceOp.SUM, group=self.group)
+        synced = self._acc_base + local
+        self.mean_2d_grad_accum, self.cnt = synced[0].contiguous(), synced[1].contiguous()
+        self._acc_base = synced.clone()
+        dist.all_reduce(self.max_radii2d, op=dist.ReduceOp.MAX, group=self.group)
+
+    def _mark_synced(self):
+        """the statistics are identical on every rank right now (after a reset / a row operation on synced values)"""
+        self._acc_base = torch.stack((self.mean_2d_grad_accum, self.cnt)).clone() if self.world_size() > 1 else None
 
     # ---- checkpoint view (gs/gaussian_splatting.py:294-339) -------------------------------------------------
     def get_params_for_save(self) -> Dict[str, torch.Tensor]:
@@ -175,6 +208,7 @@ class GaussianStore:
     def reset_densify_info(self):
         z = lambda: torch.zeros(self.N, dtype=torch.float32, device=self.device)
         self.mean_2d_grad_accum, self.cnt, self.max_radii2d = z(), z(), z()
+        self._mark_synced()
 
     def update_densify_info(self, mask: torch.Tensor, mean2d_grad: torch.Tensor, radii2d: Optional[torch.Tensor] = None):
         """One rendered view: `mask` [N] bool, `mean2d_grad` [N,2] (aux["mean2d_grad"] of render_view, zero rows for
@@ -221,6 +255,7 @@ class GaussianStore:
             setattr(self, attr, t.index_select(0, keep) if t.shape[0] == self.N else
                     torch.zeros(n_keep, dtype=torch.float32, device=self.device))
         self.N = n_keep
+        self._mark_synced()  # callers synchronise before selecting rows, so the re-sliced statistics are rank-identical
         self._make_leaves()
         return n_pruned
 
@@ -254,7 +289,12 @@ class GaussianStore:
         new_mean, new_qvec = rep(self.params["mean"]), rep(self.params["qvec"])
         new_svec = torch.exp(rep(self.params["svec"]))
         if noise is None:
+            # the reference draws torch.randn here (:576-579); replicas of the view-parallel mode must draw the SAME
+            # numbers or they diverge silently (N still matches): rank 0 draws, everybody receives
             noise = torch.randn(n_sel * n_splits, 3, device=self.device)
+            if self.world_size() > 1:
+                src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+                dist.broadcast(noise, src=src, group=self.group)
         elif callable(noise):
             noise = noise(n_sel * n_splits)
         if noise.shape[0] != n_sel * n_splits:
@@ -313,6 +353,7 @@ class GaussianStore:
             return None
         if step < get("warm_up") or step > get("end") or not step_check(step, get("period"), True):
             return None
+        self.sync_densify_info()  # view-parallel replicas: the selection below must see the whole batch's statistics
         kind = get("type", "official")
         if kind == "official":
             res = self.densify_official(get("mean2d_thresh"), get("split_thresh"), get("n_splits", 2),
@@ -340,4 +381,5 @@ class GaussianStore:
             return None
         if step < get("warm_up") or step > get("end") or not step_check(step, get("period")):
             return None
+        self.sync_densify_info()
         return self.prune(get("radii2d_thresh", 0.0), get("alpha_thresh", 0.0), get("radii3d_thresh", 0.0) or 0.0)

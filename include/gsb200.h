@@ -34,6 +34,7 @@ extern "C" {
 #define GSB200_ERR_CUDA 2        /* CUDA runtime / launch error                                   */
 #define GSB200_ERR_UNSUPPORTED 3 /* e.g. tile_size != 16, SH C outside 1..4 (render.cu:507-545)   */
 #define GSB200_ERR_MISMATCH 4    /* duplicate count != gaussian_ids size (aabb_culling.h:228)      */
+#define GSB200_ERR_OVERFLOW 5    /* asynchronous-count mode: the view's tile lists exceeded the capacity */
 
 typedef struct gsb200_ctx gsb200_ctx; /* per-device scratch arena + saved state of one view       */
 typedef void* gsb200_stream;           /* cudaStream_t                                              */
@@ -42,6 +43,22 @@ const char* gsb200_last_error(void);
 int gsb200_version(void);
 int gsb200_ctx_create(int device, gsb200_ctx** out);
 int gsb200_ctx_destroy(gsb200_ctx* ctx);
+
+/* Per-context options.
+ *   GSB200_OPT_BWD_SH_VARIANT  0 (default): SH backward flushes a warp's partial sums straight to global memory with
+ *                              vector reductions (csrc/composite_bwd_sh.cu); 1: round-1 kernel (per-batch shared
+ *                              accumulator).  Both implement vol_render_sh.h:353-455; kept switchable for A/B timing.
+ *   GSB200_OPT_ASYNC_COUNT     0 (default): gsb200_render_forward waits for the view's duplicate count (8 bytes; the
+ *                              one host wait of a view -- the reference blocks twice, gs/culling.py:33-35 and
+ *                              aabb_culling.h:227).  1: no host wait: the tile sort covers a capacity learnt from the
+ *                              earlier views of this context (largest N_with_dub seen + 1/8; the first view of a
+ *                              context, or after N / the image size changed, is synchronous), *h_num_dup is -1, and the
+ *                              exact count is consumed by gsb200_render_backward / gsb200_view_stats, which return
+ *                              GSB200_ERR_OVERFLOW if the view did not fit (render it again: the capacity was raised).
+ */
+#define GSB200_OPT_BWD_SH_VARIANT 1
+#define GSB200_OPT_ASYNC_COUNT 2
+int gsb200_ctx_set_option(gsb200_ctx* ctx, int option, int64_t value);
 
 /* ================================================================================================
  * Part 1 -- one entry point per hot-path function of the reference `_gs` module, same argument
@@ -203,7 +220,8 @@ typedef struct gsb200_view_out {
   float* depthg;   /* [N]                                                                         */
   uint8_t* mask;   /* [N]                                                                         */
   float* radii2d;  /* [N] or NULL: m + sqrt(max(m^2-det,0)) (gaussian_splatting.py:1240-1245)     */
-  int64_t* h_num_dup; /* host out (nullable): N_with_dub                                           */
+  int64_t* h_num_dup; /* host out (nullable): N_with_dub (-1 in asynchronous-count mode)           */
+  int64_t* h_generation; /* host out (nullable): stamp of this forward; pass it to render_backward   */
 } gsb200_view_out;
 
 int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* cam, const gsb200_view_in* in,
@@ -230,6 +248,8 @@ typedef struct gsb200_view_grads {
                     /*                gaussian_splatting.py:464-469)                                */
   float* g_bg;      /* [H,W,3] or NULL: nan_to_num(g_rgb * T) (gs/renderer.py:1282)                 */
   int32_t accumulate;
+  int64_t generation; /* 0 = unchecked; else must equal the stamp render_forward returned: a context holds the  */
+                      /* binning + splat records of ONE view, and a later forward on it overwrites them           */
 } gsb200_view_grads;
 
 int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* cam, const gsb200_view_in* in,
@@ -246,8 +266,10 @@ int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* cam, const gsb2
 int gsb200_ctx_set_profiling(gsb200_ctx* ctx, int enable);
 int gsb200_ctx_get_profile(gsb200_ctx* ctx, float* h_ms /*[6]*/, int64_t* h_counts /*[5]*/, int reset);
 
-/* per-view statistics of the last forward on ctx (synchronises): h_out[0]=N_with_dub,
- * h_out[1]=number of Gaussians passing the frustum test, h_out[2]=max tile list length */
+/* per-view statistics of the last forward on ctx (synchronises the stream): h_out[0]=N_with_dub,
+ * h_out[1]=number of Gaussians passing the frustum test, h_out[2]=longest tile list.  In asynchronous-count
+ * mode this is where a forward-only caller learns the count; returns GSB200_ERR_OVERFLOW (numbers valid) when
+ * the view's lists were truncated. */
 int gsb200_view_stats(gsb200_ctx* ctx, int64_t* h_out, gsb200_stream stream);
 
 /* ================================================================================================

@@ -66,18 +66,21 @@ class _Vpr:
         self.n_reduce += 1
 
 
-def _setup(n_views=2, H=8, W=6):
+def _setup(n_views=2, H=8, W=6, world=1, n=5):
     cams = [types.SimpleNamespace(h=H, w=W) for _ in range(n_views)]
     c2ws = [torch.eye(4)[:3] * (v + 1) for v in range(n_views)]
-    gouts = [torch.randn(H, W, 3) for _ in range(n_views)]
+    gouts = {v: torch.randn(H, W, 3) for v in range(n_views)}
     calls = []
 
-    def render_view(mean, qvec, svec, alpha, c2w, cam, sh=None, C=1, slot=0, grad_sink=None):
+    def render_view(mean, qvec, svec, alpha, c2w, cam, sh=None, C=1, slot=0, grad_sink=None, async_count=False):
         calls.append((slot, grad_sink is not None, torch.is_grad_enabled()))
         img = (sh.sum() * 0 + c2w[0, 0]) * torch.ones(cam.h, cam.w, 3) + mean.sum() * 0
         return {"rgb": img}
 
-    return cams, c2ws, gouts, render_view, calls
+    w = types.SimpleNamespace(vpr=_Vpr(n), mine=list(range(n_views)), cams=cams, c2ws_cpu=c2ws, C=2,
+                              slot_of={v: v for v in range(n_views)}, dev="cpu", world=world, render_view=render_view,
+                              gouts=gouts, async_count=False, n_views=n_views, scene=types.SimpleNamespace(N=n))
+    return w, calls
 
 
 @pytest.mark.parametrize("world", [1, 2])
@@ -85,38 +88,48 @@ def test_measure_e2e_bookkeeping(bench_mod, monkeypatch, world):
     import torch.distributed as dist
 
     monkeypatch.setattr(dist, "all_reduce", lambda t, op=None, group=None: None)
-    cams, c2ws, gouts, render_view, calls = _setup()
-    vpr = _Vpr(5)
+    w, calls = _setup(world=world)
     args = types.SimpleNamespace(steps=4)
-    mine = [0, 1]
     barriers = []
-    e2e = bench_mod.measure_e2e(args, vpr, mine, render_view, c2ws, cams, gouts, 2, {0: 0, 1: 1}, 5, 2, world, "cpu",
-                                lambda: barriers.append(1))
+    e2e = bench_mod.measure_e2e(args, w, lambda: barriers.append(1))
     H, W = 8, 6
     assert e2e["h2d_bytes_per_step"] == 2 * (H * W * 3 * 4 + 240) and e2e["d2h_bytes_per_step"] == 2 * H * W * 3 * 4
     assert e2e["ms_per_step"] == 50.0 / 4 and len(e2e["ms_per_step_all_runs"]) == 3
     assert e2e["value"] == pytest.approx(2 * 5 * H * W / (12.5e-3))
-    loops = 1 if world > 1 else 2  # the side-stream schedule runs at world_size 1 only
-    assert vpr.n_zero == vpr.n_reduce == loops * (3 + 3 * 4)
+    loops = 2  # single-stream schedule, then the side-stream schedule (all world sizes since round 2)
+    assert w.vpr.n_zero == w.vpr.n_reduce == loops * (3 + 3 * 4)
     assert len(barriers) == loops * 6
-    if world == 1:
-        assert e2e["copy_schedule"].startswith("copies on side streams") and e2e["side_stream_error"] is None
-        assert calls[-1][2] is False  # the image check re-renders under no_grad
-    else:
-        assert e2e["copy_schedule"] == "copies on the launching stream" and "world_size" in e2e["side_stream_error"]
+    assert e2e["copy_schedule"].startswith("copies on side streams") and e2e["side_stream_error"] is None
+    assert calls[-1][2] is False  # the image check re-renders under no_grad
     assert all(c[1] for c in calls[:-1])  # every timed call accumulates into the flat gradient buffer
 
 
 def test_measure_e2e_falls_back_when_the_host_image_is_wrong(bench_mod):
-    cams, c2ws, gouts, render_view, calls = _setup(n_views=1)
+    w, calls = _setup(n_views=1, n=3)
     n = [0]
+    inner = w.render_view
 
     def drifting(*a, **kw):  # every call returns a different image: the D2H check of the side-stream schedule fails
         n[0] += 1
-        out = render_view(*a, **kw)
+        out = inner(*a, **kw)
         return {"rgb": out["rgb"] + n[0]}
 
-    e2e = bench_mod.measure_e2e(types.SimpleNamespace(steps=2), _Vpr(3), [0], drifting, c2ws, cams, gouts, 2, {0: 0}, 3,
-                                1, 1, "cpu", lambda: None)
+    w.render_view = drifting
+    e2e = bench_mod.measure_e2e(types.SimpleNamespace(steps=2), w, lambda: None)
     assert e2e["copy_schedule"] == "copies on the launching stream"
     assert "differs" in e2e["side_stream_error"] and e2e["value"] > 0
+
+
+def test_reference_arm_sets_its_thread_count(monkeypatch):
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arm must override it (round-1 SCALE runs at N >= 2 timed
+    the reference on ONE core)."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, os; sys.argv=['bench.py','--impl','reference']; os.environ['OMP_NUM_THREADS']='1'; "
+            "import importlib.util as u; sp=u.spec_from_file_location('b', %r); m=u.module_from_spec(sp); "
+            "sp.loader.exec_module(m); print(os.environ['OMP_NUM_THREADS'], m.usable_cpus())" % os.path.join(root, "bench.py"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    got, want = out.stdout.split()[-2:]
+    assert got == want, out.stdout + out.stderr

@@ -20,11 +20,22 @@ def test_shard_views_round_robin():
 
 
 def test_field_layout_sizes():
+    from gsgen_b200.parallel import layout_total
+
     lay = field_layout(10, 4)
     assert [l[0] for l in lay] == ["mean", "qvec", "svec", "alpha", "sh"]
-    assert lay[-1][2] + lay[-1][3] == 10 * (3 + 4 + 3 + 1 + 48)  # 59 floats = 236 B / Gaussian at SH degree 3
+    assert sum(l[3] for l in lay) == 10 * (3 + 4 + 3 + 1 + 48)  # 59 floats = 236 B / Gaussian at SH degree 3
     assert field_layout(10, None)[-1][0] == "color"
-    assert field_layout(10, None)[-1][2] + 30 == 10 * 14  # 56 B / Gaussian RGB
+    assert sum(l[3] for l in field_layout(10, None)) == 10 * 14  # 56 B / Gaussian RGB
+    # every field starts on a 16-byte boundary whatever N is (float4 accesses to qvec / g_qvec; round-1 advice)
+    for N in (1, 2, 3, 5, 10, 4097, 6145):
+        for C in (None, 1, 3, 4):
+            lay = field_layout(N, C)
+            assert all(off % 4 == 0 for _, _, off, _ in lay), (N, C)
+            assert all(lay[i][2] + lay[i][3] <= lay[i + 1][2] for i in range(len(lay) - 1))
+            assert layout_total(lay) % 4 == 0 and layout_total(lay) - (lay[-1][2] + lay[-1][3]) < 4
+    # with N % 4 == 0 there is no padding: the buffer is exactly the 236 B / Gaussian the all-reduce is quoted at
+    assert layout_total(field_layout(1000, 4)) == 1000 * 59
 
 
 def _scene_and_views():

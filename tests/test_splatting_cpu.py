@@ -32,7 +32,7 @@ class _Aux(dict):
 def _oracle_render_fn(oracle_mod):
     def render_fn(mean, qvec, svec, alpha, c2w, cam, color=None, bg=None, rgb_only=False, raw_params=False,
                   frustum_radius=6.0, tile_radius=6.0, T_thresh=1e-4, skip_frustum_culling=False, depth_detach=True,
-                  grad_sink=None):
+                  grad_sink=None, slot=0):
         assert raw_params and not skip_frustum_culling
         out = oracle_mod.render_view(mean, qvec, torch.exp(svec), torch.sigmoid(alpha), c2w, ocam_of(cam),
                                      color=torch.sigmoid(color), bg=bg, rgb_only=rgb_only, depth_detach=depth_detach,
