@@ -30,6 +30,17 @@ class CameraInfo:
         """`CameraPoseProvider` convention (data/__init__.py:188-197): fx=fy=focal*reso, cx=cy=reso/2."""
         return cls(focal * reso, focal * reso, reso / 2.0, reso / 2.0, reso, reso, near_plane, far_plane)
 
+    @classmethod
+    def from_fov_camera(cls, fov, aspect, resolution, near_plane, far_plane):
+        """utils/camera.py:316-325 (the viewer's camera: vertical fov in radians, width = `resolution`)"""
+        W = resolution
+        H = int(resolution / aspect)
+        cx = W / 2
+        cy = H / 2
+        fx = cx / np.tan(fov / 2)
+        fy = cy / np.tan(fov / 2)
+        return cls(fx, fy, cx, cy, W, H, near_plane, far_plane)
+
     def get_frustum(self, c2w: torch.Tensor):
         """-> (normals[6,3], pts[6,3]) fp32 on c2w's device; reference utils/camera.py:260-294."""
         up = -c2w[:, 1]

@@ -13,8 +13,8 @@
 //     L2 float atomics are fire-and-forget and aggregate in the 126 MB L2; the (Gaussian, tile) instance is reduced
 //     there instead of in shared memory.
 //   * ONE block barrier per batch (like the forward): it retires the staging buffer and votes on early termination.
-//   * product mapping: lane = (k-quad kq, row group rg); per 4 pixels a lane issues 4 LDS.128 of the basis (rows
-//     4kq..4kq+3) + 2 LDS.128 of the per-pixel factors (rows rg, rg+8) for 16 FFMA2 -- 6 : 16 instead of 7 : 12.
+//   * product mapping: lane = (pixel half, k-quad, row group): 96 units of work, exactly 3 per lane, 7 LDS.128 per
+//     24 FFMA2 (round 1: 7 per 12); see flush_direct.
 #include "composite_common.cuh"
 
 namespace gsb {
@@ -22,25 +22,18 @@ namespace gsb {
 template <int C> struct ShBwdTraits {
   static constexpr int CC = C * C;
   static constexpr int kG = 4;                          // hits per flush
-  static constexpr int kRows = 3 * kG;                  // SH rows of a flush (hit*3 + channel)
-  static constexpr int kKQ = (CC <= 4) ? 1 : 4;         // k-quads (4 coefficients each) spread over the lanes
+  static constexpr int kRows = 3 * kG;                  // SH rows of a flush (hit*3 + channel) = 12
+  // product mapping: lane = (pixel part p [kPH], k-quad kq [kKQ], hit h [4]); a lane owns the hit's 3 channel rows
+  static constexpr int kKQ = (CC <= 4) ? 1 : 4;         // k-quads (4 coefficients each)
   static constexpr int kKL = 4 * kKQ;                   // basis rows held in shared memory (zero beyond CC)
-  static constexpr int kRG = 32 / kKQ;                  // row groups
-  static constexpr int kNR = (kRows + kRG - 1) / kRG;   // rows per lane
+  static constexpr int kPH = 8 / kKQ;                   // pixel parts (2 for C >= 3, 8 for C = 2)
+  static constexpr int kNG = 8 / kPH;                   // 16-byte pixel groups per lane (4 or 1)
   static constexpr int kTFloats = kG * 9 * 32;          // per warp: [kRows + 6*kG][32 px]
   static constexpr int kYFloats = kKL * 32;             // per warp: basis [k][32 px]
   static constexpr int kWarpFloats = kTFloats + kYFloats;
   static constexpr bool kVec4 = (CC % 4 == 0);          // g_sh rows are 16-byte granular
 };
 
-// physical 16-byte group of logical pixel group q in a transpose-buffer row / basis row (bank-conflict-free reads:
-// the 8 row groups of a product step read rows r, r+1, .. r+7; the 4 k-quads read basis rows 4kq + i)
-__device__ __forceinline__ int t_group(int q, int row) { return (q + row) & 7; }
-__device__ __forceinline__ int y_group(int q, int k) { return (q + 2 * (k >> 2) + (k & 3)) & 7; }
-
-// Flush of a warp's transpose buffer.  SH rows [hit*3+c][32 px] x basis Ysm[k][px] -> g_sh partial sums (vector
-// reduction to global memory); geometry rows -> row sums -> the Gaussian's gradient record (fused) or the
-// reference-layout grad_mean / grad_cov / grad_alpha tensors.
 struct FlushDst {  // by value: a reference to the kernel's argument struct would force a local-memory copy of it
   float* pay;      // g_sh [N,3,C*C]
   float* g0;       // fused: gradient records [N,8];  else grad_mean [N,2]
@@ -48,75 +41,102 @@ struct FlushDst {  // by value: a reference to the kernel's argument struct woul
   float* g2;       // else grad_alpha [N]
 };
 
+// 16-byte shared-memory load with base + compile-time immediate addressing
+template <int IMM> __device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];\n"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr), "n"(IMM));
+  return v;
+}
+
+// Flush of a warp's transpose buffer.  SH rows T[hit*3+c][32 px] x basis Ysm[k][32 px] -> g_sh partial sums; geometry
+// rows -> row sums -> the Gaussian's gradient record (fused) or the reference-layout grad_mean / grad_cov / grad_alpha.
+//
+// Product (C >= 3): 4 hits x 3 channels x 4 k-quads x 2 pixel halves = 96 units of (4 coefficients x 16 pixels),
+// exactly 3 per lane: lane = (p, kq, h) owns hit h's three channel rows, k-quad kq, pixel half p -- no division to
+// find (hit, channel), one id look-up per lane, and the three reductions of a lane differ by an immediate offset.
+// Per 4 pixels a lane issues 4 LDS.128 of the basis + 3 LDS.128 of the per-pixel factors for 24 FFMA2 (round 1: 7 LDS
+// for 12 FFMA2) and no FMA is wasted.  Both buffers are stored UNROTATED (the hit loop's stores are base + immediate);
+// at step q a lane reads pixel group 4p + (kq ^ q): the 8 (p, kq) combinations of a quarter-warp land on 8 different
+// 16-byte groups -> no bank conflict on the basis rows (same 128-byte alignment), lanes sharing a factor row broadcast,
+// and because rows are 128-byte aligned the address is (base ^ (q << 4)) + immediate: 3 LOP3 per buffer and flush.
+// The pixel parts are combined with one shuffle per value and ONE lane per (hit, k-quad) sends 4 consecutive
+// coefficients per channel with red.global.add.v4.f32.
 template <int C, bool FUSED>
 __device__ __noinline__ void flush_direct(const FlushDst a, const float* my_t, const float* my_y,
                                           const int* ids_stage, int nslot, unsigned slots, int lane) {
   using ST = ShBwdTraits<C>;
   constexpr int CC = ST::CC;
-  const int kq = lane & (ST::kKQ - 1);
-  const int rg = lane / ST::kKQ;
+  const int p = lane & (ST::kPH - 1);
+  const int kq = (lane / ST::kPH) & (ST::kKQ - 1);
+  const int h = lane / (ST::kPH * ST::kKQ);  // 0..3
   __syncwarp();
-  float acc[ST::kNR][4], aco[ST::kNR][4];  // even / odd pixel partial sums (FFMA2)
+  float acc[3][4], aco[3][4];  // [channel][k in quad]: even / odd pixel partial sums (FFMA2)
 #pragma unroll
-  for (int i = 0; i < ST::kNR; ++i)
+  for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; aco[i][j] = 0.f; }
-#pragma unroll 2
-  for (int q = 0; q < 8; ++q) {
-    float4 y4[4];
+  const uint32_t g0 = (uint32_t)(p * ST::kNG + (ST::kNG == 4 ? kq : 0)) << 4;   // byte offset of the lane's first group
+  const uint32_t at = smem_u32(my_t) + (uint32_t)h * (3 * 128) + g0;             // rows 3h, 3h+1, 3h+2 at +0/+128/+256
+  const uint32_t ay = smem_u32(my_y) + (uint32_t)kq * (4 * 128) + g0;            // rows 4kq .. 4kq+3
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = 4 * kq + j;
-      y4[j] = *reinterpret_cast<const float4*>(my_y + k * 32 + 4 * y_group(q, k));
-    }
+  for (int q = 0; q < ST::kNG; ++q) {
+    const uint32_t atq = at ^ (uint32_t)(q << 4), ayq = ay ^ (uint32_t)(q << 4);
+    const float4 y0 = lds128<0>(ayq), y1 = lds128<128>(ayq), y2 = lds128<256>(ayq), y3 = lds128<384>(ayq);
+    const float4 t0 = lds128<0>(atq), t1 = lds128<128>(atq), t2 = lds128<256>(atq);
+    const float4 ts[3] = {t0, t1, t2};
+    const float4 ys[4] = {y0, y1, y2, y3};
 #pragma unroll
-    for (int i = 0; i < ST::kNR; ++i) {
-      const int row = rg + i * ST::kRG;
-      if (ST::kNR * ST::kRG > ST::kRows && row >= ST::kRows) continue;  // (compile-time false when rows tile exactly)
-      const float4 t = *reinterpret_cast<const float4*>(my_t + row * 32 + 4 * t_group(q, row));
+    for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        ffma2(acc[i][j], aco[i][j], t.x, t.y, y4[j].x, y4[j].y);
-        ffma2(acc[i][j], aco[i][j], t.z, t.w, y4[j].z, y4[j].w);
+        ffma2(acc[i][j], aco[i][j], ts[i].x, ts[i].y, ys[j].x, ys[j].y);
+        ffma2(acc[i][j], aco[i][j], ts[i].z, ts[i].w, ys[j].z, ys[j].w);
       }
-    }
   }
+  float v[3][4];
 #pragma unroll
-  for (int i = 0; i < ST::kNR; ++i) {
-    const int row = rg + i * ST::kRG;
-    if (row < nslot * 3) {
-      const int h = row / 3, c = row - 3 * h;
-      const int id = ids_stage[(slots >> (8 * h)) & 255u];
-      float* dst = a.pay + (size_t)id * (3 * CC) + c * CC + 4 * kq;
-      const float v0 = acc[i][0] + aco[i][0], v1 = acc[i][1] + aco[i][1];
-      const float v2 = acc[i][2] + aco[i][2], v3 = acc[i][3] + aco[i][3];
-      if (ST::kVec4 && ((reinterpret_cast<uintptr_t>(a.pay) & 15) == 0)) {
-        red_add_v4(dst, v0, v1, v2, v3);
-      } else {
-        if (4 * kq + 0 < CC) red_add(dst + 0, v0);
-        if (4 * kq + 1 < CC) red_add(dst + 1, v1);
-        if (4 * kq + 2 < CC) red_add(dst + 2, v2);
-        if (4 * kq + 3 < CC) red_add(dst + 3, v3);
-      }
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[i][j] = acc[i][j] + aco[i][j];
+#pragma unroll
+      for (int x = 1; x < ST::kPH; x <<= 1) v[i][j] += __shfl_xor_sync(kFull, v[i][j], x);  // the other pixel parts
+    }
+  if (p == 0 && h < nslot) {
+    const int id = ids_stage[(slots >> (8 * h)) & 255u];
+    float* dst = a.pay + (size_t)id * (3 * CC) + 4 * kq;
+    if (ST::kVec4 && ((reinterpret_cast<uintptr_t>(a.pay) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) red_add_v4(dst + i * CC, v[i][0], v[i][1], v[i][2], v[i][3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (4 * kq + j < CC) red_add(dst + i * CC + j, v[i][j]);
     }
   }
-  // geometry: row sums, one row per lane (lane = hit*6 + value), then gathered into the hit's first lane
-  float s = 0.f;
+  // geometry: row sums, one row per lane (lane = hit*6 + value; at step q the lane reads 16-byte group q ^ (lane & 7):
+  // conflict-free), then gathered into the hit's first lane
+  float se = 0.f, so = 0.f;
   if (lane < nslot * 6) {
-    const int row = ST::kRows + lane;
-    const float* base = my_t + row * 32;
+    const uint32_t ag = smem_u32(my_t) + (uint32_t)(ST::kRows + lane) * 128 + ((uint32_t)(lane & 7) << 4);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float4 t = *reinterpret_cast<const float4*>(base + 4 * t_group(q, row));
-      s += (t.x + t.y) + (t.z + t.w);
+      const float4 t = lds128<0>(ag ^ (uint32_t)(q << 4));
+      ffma2(se, so, t.x, t.y, 1.0f, 1.0f);
+      ffma2(se, so, t.z, t.w, 1.0f, 1.0f);
     }
   }
+  const float s = se + so;
   const float s1 = __shfl_down_sync(kFull, s, 1), s2 = __shfl_down_sync(kFull, s, 2);
   const float s3 = __shfl_down_sync(kFull, s, 3), s4 = __shfl_down_sync(kFull, s, 4);
   const float s5 = __shfl_down_sync(kFull, s, 5);
   if (lane < nslot * 6 && (lane % 6) == 0) {
-    const int h = lane / 6;
-    const int id = ids_stage[(slots >> (8 * h)) & 255u];
+    const int hh = lane / 6;
+    const int id = ids_stage[(slots >> (8 * hh)) & 255u];
     if constexpr (FUSED) {  // {gmx, gmy, gxx, gxy | gyy, galpha, gdepth, -}
       red_add_v4(a.g0 + (size_t)id * 8, s, s1, s2, s3);
       red_add_v2(a.g0 + (size_t)id * 8 + 4, s4, s5);
@@ -131,6 +151,9 @@ __device__ __noinline__ void flush_direct(const FlushDst a, const float* my_t, c
 
 #ifndef GSB_BWDSH_B
 #define GSB_BWDSH_B 32  // list entries per staged batch
+#endif
+#ifndef GSB_BWDSH_PREFETCH
+#define GSB_BWDSH_PREFETCH 0  // 1: hit-loop software pipeline (next record fetched while the current one is evaluated); measured round 2: 1.028 ms with, 1.013 ms without (C3)
 #endif
 #ifndef GSB_BWDSH_MINBLOCKS
 #define GSB_BWDSH_MINBLOCKS 3
@@ -186,12 +209,11 @@ k_composite_bwd_sh(const CompositeArgs a) {
     sh_basis<C>(d[0], d[1], d[2], Y);
   }
   // per-warp transpose buffer: SH rows [G*3][32] (row = hit*3 + channel), geometry rows [G*6][32], then the block's
-  // basis matrix Ysm[k][32] (k-major); 16-byte groups rotated per row (t_group / y_group)
+  // basis matrix Ysm[k][32] (k-major); everything unrotated, the reader picks conflict-free groups (flush_direct)
   float* my_t = s_tbuf + warp * ST::kWarpFloats;
   float* my_y = my_t + ST::kTFloats;
 #pragma unroll
-  for (int k = 0; k < ST::kKL; ++k)
-    my_y[k * 32 + 4 * y_group(lane >> 2, k) + (lane & 3)] = (k < CC) ? Y[k < CC ? k : 0] : 0.f;
+  for (int k = 0; k < ST::kKL; ++k) my_y[k * 32 + lane] = (k < CC) ? Y[k < CC ? k : 0] : 0.f;
   __syncwarp();
   int nslot = 0;        // hits buffered in my_t (warp-uniform)
   unsigned slots = 0u;  // their batch entry indices, 8 bits each
@@ -239,14 +261,22 @@ k_composite_bwd_sh(const CompositeArgs a) {
         bool hit = false;
         if (j < cnt) hit = splat_hits_block(sg0[j], sg1[j], pg);
         unsigned m = __ballot_sync(kFull, hit);
+#if GSB_BWDSH_PREFETCH
         // software pipeline over the hits: the next hit's record is fetched while the current one is evaluated
         int bitn = __ffs(m) - 1;
         float4 n0 = sg0[m ? r * 32 + bitn : 0], n1 = sg1[m ? r * 32 + bitn : 0];
+#endif
         while (m) {
+#if GSB_BWDSH_PREFETCH
           const int jj = r * 32 + bitn;
           const float4 g0 = n0, g1 = n1;
           m &= m - 1;
           if (m) { bitn = __ffs(m) - 1; n0 = sg0[r * 32 + bitn]; n1 = sg1[r * 32 + bitn]; }
+#else
+          const int jj = r * 32 + (__ffs(m) - 1);
+          m &= m - 1;
+          const float4 g0 = sg0[jj], g1 = sg1[jj];
+#endif
           float G, u, v;
           const float aG = splat_aG(g0, g1, pg.px, pg.py, &G, &u, &v);
           const bool ok = !done && (aG >= kMinRenderAlpha);
@@ -294,17 +324,10 @@ k_composite_bwd_sh(const CompositeArgs a) {
             done = T < a.thresh;
           }
           {
-            const int r0 = nslot * 3, g0r = ST::kRows + nslot * 6;
-            const int pg4 = lane >> 2, pe = lane & 3;
-            my_t[(r0 + 0) * 32 + 4 * t_group(pg4, r0 + 0) + pe] = t0;
-            my_t[(r0 + 1) * 32 + 4 * t_group(pg4, r0 + 1) + pe] = t1;
-            my_t[(r0 + 2) * 32 + 4 * t_group(pg4, r0 + 2) + pe] = t2;
-            my_t[(g0r + 0) * 32 + 4 * t_group(pg4, g0r + 0) + pe] = e0;
-            my_t[(g0r + 1) * 32 + 4 * t_group(pg4, g0r + 1) + pe] = e1;
-            my_t[(g0r + 2) * 32 + 4 * t_group(pg4, g0r + 2) + pe] = e2;
-            my_t[(g0r + 3) * 32 + 4 * t_group(pg4, g0r + 3) + pe] = e3;
-            my_t[(g0r + 4) * 32 + 4 * t_group(pg4, g0r + 4) + pe] = e4;
-            my_t[(g0r + 5) * 32 + 4 * t_group(pg4, g0r + 5) + pe] = e5;
+            float* rs = my_t + nslot * (3 * 32) + lane;                  // SH rows of this hit
+            float* rgm = my_t + (ST::kRows + nslot * 6) * 32 + lane;     // geometry rows of this hit
+            rs[0] = t0; rs[32] = t1; rs[64] = t2;
+            rgm[0] = e0; rgm[32] = e1; rgm[64] = e2; rgm[96] = e3; rgm[128] = e4; rgm[160] = e5;
             slots |= (unsigned)jj << (8 * nslot);
             if (++nslot == ST::kG) {
               flush_direct<C, FUSED>(dst, my_t, my_y, sids, nslot, slots, lane);

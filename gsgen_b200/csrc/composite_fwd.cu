@@ -15,8 +15,20 @@
 
 namespace gsb {
 
+#ifndef GSB_FWD_B
+#define GSB_FWD_B 64        // list entries per staged batch for SH degree >= 2
+#endif
+#ifndef GSB_FWD_MINBLOCKS
+#define GSB_FWD_MINBLOCKS 0  // 0: no minBlocksPerSM hint (48 registers at SH deg 3 -> 5 CTAs/SM).  Note: a hint of 1 is
+#endif                       // NOT neutral -- ptxas then spends 81 registers (3 CTAs/SM); 6 caps it at 40.
+#if GSB_FWD_MINBLOCKS > 0
+#define GSB_FWD_BOUNDS __launch_bounds__(kCtaThreads, GSB_FWD_MINBLOCKS)
+#else
+#define GSB_FWD_BOUNDS __launch_bounds__(kCtaThreads)
+#endif
+
 template <int PAY, int C, bool EXTRAS, int B>
-__global__ void __launch_bounds__(kCtaThreads)
+__global__ void GSB_FWD_BOUNDS
 k_composite_fwd(const CompositeArgs a) {
   using L = StageLayout<PAY, C, B, false>;
   using PT = PayTraits<PAY, C>;
@@ -240,8 +252,8 @@ int launch_composite_fwd(int pay_kind, int C, bool extras, const CompositeArgs& 
       switch (C) {
         case 1: return launch_one<PAY_SH, 1, false, 256>(a, st);
         case 2: return launch_one<PAY_SH, 2, false, 256>(a, st);
-        case 3: return launch_one<PAY_SH, 3, false, 64>(a, st);
-        case 4: return launch_one<PAY_SH, 4, false, 64>(a, st);
+        case 3: return launch_one<PAY_SH, 3, false, GSB_FWD_B>(a, st);
+        case 4: return launch_one<PAY_SH, 4, false, GSB_FWD_B>(a, st);
         default: break;
       }
     default: break;

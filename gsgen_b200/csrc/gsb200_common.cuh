@@ -78,6 +78,7 @@ struct gsb200_ctx {
   // host-visible scalars
   int64_t* h_total = nullptr;  // pinned [4]: duplicates, visible Gaussians, overflow flag, max list length
   gsb::Buf d_total;            // unsigned long long[2] device-side counters (duplicates, visible Gaussians)
+  gsb::Buf d_small;            // int32[4] scratch scalars of the store movers (store.cu)
   gsb::Buf d_overflow;         // int32[2]: [0] tile-list capacity overflow flag (async-count mode), [1] max list length
   cudaEvent_t ev_total = nullptr;
   // options (gsb200_ctx_set_option)
@@ -160,7 +161,9 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};\n" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
-__device__ __forceinline__ void red_add(float* addr, float a) { atomicAdd(addr, a); }
+__device__ __forceinline__ void red_add(float* addr, float a) {  // (atomicAdd on a pointer of unknown address space
+  asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(addr), "f"(a) : "memory");  // compiles to generic ATOM + QSPC)
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

@@ -110,6 +110,9 @@ class FlatAdam:
             nxt = self.layout[i + 1][2] if i + 1 < len(self.layout) else total
             if nxt < off + n:
                 raise RuntimeError("layout fields overlap or exceed the buffer")
+            if nxt - (off + n) >= 4:  # only 16-byte alignment padding may separate fields (parallel.field_layout)
+                raise RuntimeError(f"layout leaves {nxt - (off + n)} unowned floats after field {i}: fields must tile "
+                                   "the buffer up to alignment padding")
             self._fields[i].begin, self._fields[i].count = off, nxt - off
 
     def lr_at(self, step: int) -> Dict[str, float]:

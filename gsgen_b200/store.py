@@ -17,8 +17,10 @@ layout (`field_layout(capacity, C)`): field f occupies `capacity * width_f` floa
 The live gradient rows are what the multi-GPU step all-reduces; `gsgen_b200.optim.FlatAdam` steps the whole arena in
 one kernel (dead rows carry zero gradients and zero moments, so they do not move).
 
-Row movers are torch indexing ops on the device the buffers live on (they are HBM-bound gathers; a hand-written mover
-is a later step) -- this file is host logic like `parallel.py` and is exercised on CPU tensors by the test-suite.
+Row movers: on a CUDA device the two hand-written kernels of csrc/store.cu (`gsb200_store_compact`: prefix sum + ONE
+launch that moves all fields of all four buffers into the arena's shadow buffers, which are then swapped in;
+`gsb200_store_append`: one launch).  On CPU tensors (the test-suite exercises this host logic without a GPU) the same
+row operations are torch indexing ops; `tests/test_store_gpu.py` checks the kernels against that path bit for bit.
 Selection rules follow the reference bit for bit, including two quirks that a drop-in must keep:
   * `densify_by_clone` compares `torch.norm(grads, dim=-1)` of the 1-D per-Gaussian statistic, i.e. ONE number for the
     whole scene, with the threshold (:616-618);
@@ -80,6 +82,7 @@ class GaussianStore:
     def _alloc(self, cap: int):
         cap = self._round_cap(cap)
         self.cap = cap
+        self._shadow = None  # second set of buffers the CUDA compaction writes into (allocated at the first prune)
         self.layout = field_layout(cap, self.C)
         total = layout_total(self.layout)
         mk = lambda: torch.zeros(total, dtype=torch.float32, device=self.device)
@@ -226,10 +229,13 @@ class GaussianStore:
             return 0
         if self.N + k > self.cap:
             self._grow(self.N + k)
-        for name in self._field:
-            self._rows(self.flat_param, name, k, self.N).copy_(new_params[name].detach().reshape(k, -1))
-            for buf in (self.flat_grad, self.exp_avg, self.exp_avg_sq):
-                self._rows(buf, name, k, self.N).zero_()
+        if self.device.type == "cuda":
+            self._append_cuda(new_params, k)
+        else:
+            for name in self._field:
+                self._rows(self.flat_param, name, k, self.N).copy_(new_params[name].detach().reshape(k, -1))
+                for buf in (self.flat_grad, self.exp_avg, self.exp_avg_sq):
+                    self._rows(buf, name, k, self.N).zero_()
         self.N += k
         self._make_leaves()
         return k
@@ -239,16 +245,24 @@ class GaussianStore:
         their rows (`prune_optimizer` :421-449)."""
         if mask.shape[0] != self.N:
             raise RuntimeError(f"prune mask has {mask.shape[0]} rows, the store {self.N}")
-        keep = (~mask.to(self.device)).nonzero(as_tuple=True)[0]
-        n_keep = int(keep.shape[0])
-        if n_keep < self.N:
-            for buf in self._buffers():
-                for name in self._field:
-                    live = self._rows(buf, name, self.N)
-                    gathered = live.index_select(0, keep)  # temporary: source and destination overlap
-                    live[:n_keep].copy_(gathered)
-                    live[n_keep:].zero_()  # dead rows: zero gradient / moments, so FlatAdam leaves them alone
+        mask = mask.to(self.device)
+        if self.device.type == "cuda":
+            n_keep = self._compact_cuda(mask)
+            keep = None
+        else:
+            keep = (~mask).nonzero(as_tuple=True)[0]
+            n_keep = int(keep.shape[0])
+            if n_keep < self.N:
+                for buf in self._buffers():
+                    for name in self._field:
+                        live = self._rows(buf, name, self.N)
+                        gathered = live.index_select(0, keep)  # temporary: source and destination overlap
+                        live[:n_keep].copy_(gathered)
+                        live[n_keep:].zero_()  # dead rows: zero gradient / moments, so FlatAdam leaves them alone
         n_pruned = self.N - n_keep
+        if keep is None:  # (the three [N] statistics are re-sliced with one boolean index each)
+            keep = (~mask).nonzero(as_tuple=True)[0] if any(
+                getattr(self, a).shape[0] == self.N for a in ("max_radii2d", "mean_2d_grad_accum", "cnt")) else None
         # statistics: re-sliced when their length matches the mask, zeros otherwise (the IndexError branches)
         for attr in ("max_radii2d", "mean_2d_grad_accum", "cnt"):
             t = getattr(self, attr)
@@ -258,6 +272,57 @@ class GaussianStore:
         self._mark_synced()  # callers synchronise before selecting rows, so the re-sliced statistics are rank-identical
         self._make_leaves()
         return n_pruned
+
+    # ---- CUDA row movers (csrc/store.cu) -------------------------------------------------------------------
+    def _field_tables(self):
+        import ctypes
+
+        names = list(self._field)
+        offs = (ctypes.c_uint64 * len(names))(*[self._field[n][1] for n in names])
+        widths = []
+        for n in names:
+            w = 1
+            for s_ in self._field[n][0][1:]:
+                w *= s_
+            widths.append(w)
+        return names, offs, (ctypes.c_uint32 * len(names))(*widths)
+
+    def _compact_cuda(self, mask: torch.Tensor) -> int:
+        import ctypes
+
+        from . import _lib
+
+        if self._shadow is None:
+            self._shadow = [torch.zeros_like(b) for b in self._buffers()]
+            self._shadow_rows = 0  # rows of the shadow buffers that may hold stale (non-zero) data
+        names, offs, widths = self._field_tables()
+        bufs = list(self._buffers())
+        src = (ctypes.c_void_p * 4)(*[b.data_ptr() for b in bufs])
+        dst = (ctypes.c_void_p * 4)(*[b.data_ptr() for b in self._shadow])
+        m8 = mask.to(torch.bool).contiguous()
+        n_keep = ctypes.c_uint32(0)
+        _lib.check(_lib.lib().gsb200_store_compact(
+            _lib.ctx(self.device), src, dst, ctypes.c_int32(4), offs, widths, ctypes.c_int32(len(names)),
+            ctypes.c_uint32(self.N), ctypes.c_uint32(max(self._shadow_rows, self.N)), _lib.ptr(m8, torch.bool, "mask"),
+            ctypes.byref(n_keep), _lib.stream_ptr(self.device)))
+        # swap: the compacted copies become the arena, the old buffers (stale rows < N) the next shadow
+        self._shadow, old = bufs, self._shadow
+        self._shadow_rows = self.N
+        self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq = old
+        return int(n_keep.value)
+
+    def _append_cuda(self, new_params: Dict[str, torch.Tensor], k: int):
+        import ctypes
+
+        from . import _lib
+
+        names, offs, widths = self._field_tables()
+        rows = [new_params[n].detach().to(self.device, torch.float32).reshape(k, -1).contiguous() for n in names]
+        dst = (ctypes.c_void_p * 4)(*[b.data_ptr() for b in self._buffers()])
+        src = (ctypes.c_void_p * len(names))(*[r.data_ptr() for r in rows])
+        _lib.check(_lib.lib().gsb200_store_append(
+            _lib.ctx(self.device), dst, ctypes.c_int32(4), src, offs, widths, ctypes.c_int32(len(names)),
+            ctypes.c_uint32(self.N), ctypes.c_uint32(k), _lib.stream_ptr(self.device)))
 
     # ---- selection rules ---------------------------------------------------------------------------------
     def densify_by_clone(self, grads: torch.Tensor, grad_thresh: float, split_thresh: float,

@@ -293,6 +293,31 @@ int gsb200_adam_step(gsb200_ctx* ctx, float* param, const float* grad, float* ex
                      uint64_t total, const gsb200_adam_field* fields, int32_t n_fields /* <= 8 */, double beta1,
                      double beta2, double eps, int64_t step, float grad_scale, gsb200_stream stream);
 
+/* ================================================================================================
+ * Part 5 -- device-side row movers of the Gaussian arena.  The arena is four flat fp32 buffers
+ * (parameters, gradients, exp_avg, exp_avg_sq) with one field-major layout: field f occupies `capacity * width_f`
+ * floats starting at `field_off[f]`, its first N rows are live (gsgen_b200/store.py).
+ *
+ * gsb200_store_compact: what prune_by_mask + prune_optimizer do to every tensor and both Adam moments
+ * (gs/gaussian_splatting.py:421-449, :528-549): rows with remove_mask != 0 disappear, the order of the others is
+ * kept.  OUT OF PLACE: buffer b is read from h_src[b] and written to h_dst[b] (the arena's shadow buffer; the caller
+ * swaps them); rows [n_keep, zero_upto) of the destination are zero-filled (dead rows carry zero gradient / moments).
+ * One prefix sum + ONE mover launch for all fields of all buffers; synchronises once to return the new row count.
+ *
+ * gsb200_store_append: what densify_on_optimizer does (:481-522): k new rows behind row N of every field -- the
+ * parameter buffer h_dst[0] receives h_rows[f] ([k, width_f], device), the other buffers' new rows are zeroed
+ * (torch.cat with zeros_like).  One launch; the caller guarantees N + k <= capacity.
+ * ============================================================================================== */
+int gsb200_store_compact(gsb200_ctx* ctx, const float* const* h_src /*[n_bufs] device pointers*/,
+                         float* const* h_dst /*[n_bufs]*/, int32_t n_bufs /* <= 4 */,
+                         const uint64_t* h_field_off /*[n_fields]*/, const uint32_t* h_field_width /*[n_fields]*/,
+                         int32_t n_fields /* <= 8 */, uint32_t N, uint32_t zero_upto, const uint8_t* remove_mask /*[N]*/,
+                         uint32_t* h_n_keep, gsb200_stream stream);
+int gsb200_store_append(gsb200_ctx* ctx, float* const* h_dst /*[n_bufs]; [0] = parameters*/, int32_t n_bufs,
+                        const float* const* h_rows /*[n_fields] device pointers to [k,width_f]*/,
+                        const uint64_t* h_field_off, const uint32_t* h_field_width, int32_t n_fields, uint32_t N,
+                        uint32_t k, gsb200_stream stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -94,11 +94,11 @@ def test_measure_e2e_bookkeeping(bench_mod, monkeypatch, world):
     e2e = bench_mod.measure_e2e(args, w, lambda: barriers.append(1))
     H, W = 8, 6
     assert e2e["h2d_bytes_per_step"] == 2 * (H * W * 3 * 4 + 240) and e2e["d2h_bytes_per_step"] == 2 * H * W * 3 * 4
-    assert e2e["ms_per_step"] == 50.0 / 4 and len(e2e["ms_per_step_all_runs"]) == 3
+    assert e2e["ms_per_step"] == 50.0 / 4 and len(e2e["ms_per_step_all_runs"]) == bench_mod.N_LOOPS
     assert e2e["value"] == pytest.approx(2 * 5 * H * W / (12.5e-3))
     loops = 2  # single-stream schedule, then the side-stream schedule (all world sizes since round 2)
-    assert w.vpr.n_zero == w.vpr.n_reduce == loops * (3 + 3 * 4)
-    assert len(barriers) == loops * 6
+    assert w.vpr.n_zero == w.vpr.n_reduce == loops * (3 + bench_mod.N_LOOPS * 4)
+    assert len(barriers) == loops * 2 * bench_mod.N_LOOPS
     assert e2e["copy_schedule"].startswith("copies on side streams") and e2e["side_stream_error"] is None
     assert calls[-1][2] is False  # the image check re-renders under no_grad
     assert all(c[1] for c in calls[:-1])  # every timed call accumulates into the flat gradient buffer

@@ -71,3 +71,32 @@ def test_export_from_a_store():
     params = _params()
     st = GaussianStore(params, None, "cpu", capacity=512)
     assert export.splat_bytes(st.params) == open(os.path.join(GOLD, "ref_params_300.splat"), "rb").read()
+
+
+def test_viewer_loop_frame_equals_the_reference_expression():
+    """gsgen_b200.viewer.ViewerLoop.render_frame == the expression of ViserViewer.update (viser_viewer.py:147-155) on the
+    same rendered image, camera built by from_fov_camera (utils/camera.py:316-325) and get_c2w (viser_viewer.py:14-19)."""
+    import numpy as np
+
+    from gsgen_b200.viewer import ViewerLoop, get_c2w
+
+    seen = {}
+
+    class R:
+        def render_one(self, c2w, cam):
+            seen["c2w"], seen["cam"] = c2w, cam
+            g = torch.Generator().manual_seed(0)
+            self.img = torch.randn(cam.h, cam.w, 3, generator=g) * 0.7 + 0.5  # values below 0 and above 1 too
+            return {"rgb": self.img}
+
+    r = R()
+    loop = ViewerLoop(r, resolution=64)
+    q = np.array([0.5, 0.5, -0.5, 0.5])
+    frame = loop.render_frame(fov=0.9, aspect=1.6, wxyz=q, position=[1.0, 2.0, 3.0])
+    want = (r.img.detach().cpu().clamp(min=0.0, max=1.0).numpy() * 255.0).astype(np.uint8)
+    assert frame.dtype == np.uint8 and np.array_equal(frame, want)
+    cam = seen["cam"]
+    assert (cam.w, cam.h) == (64, int(64 / 1.6)) and abs(cam.fy - (cam.h / 2) / np.tan(0.45)) < 1e-9
+    c2w = get_c2w(q, [1.0, 2.0, 3.0])
+    assert np.allclose(c2w[:, :3] @ c2w[:, :3].T, np.eye(3), atol=1e-6) and np.allclose(c2w[:, 3], [1, 2, 3])
+    assert torch.equal(seen["c2w"], torch.from_numpy(c2w)) and loop.fps > 0

@@ -62,3 +62,34 @@ def test_sh_dc_initialisation():
     rgb = torch.rand(50, 3, generator=torch.Generator().manual_seed(0)).clamp(0.02, 0.98)
     ours = init_sh_coeffs(rgb, 4, torch.Generator().manual_seed(1), noise=0.0)
     assert torch.allclose(ours, ref(None, rgb, 4), rtol=1e-6, atol=1e-7)
+
+
+def test_viewer_camera_helpers():
+    """gsgen_b200.viewer.get_c2w / qvec2rotmat and CameraInfo.from_fov_camera against the reference's definitions
+    (utils/viewer/viser_viewer.py:14-19, utils/transforms.py:12-31, utils/camera.py:316-325)."""
+    import types
+
+    from gsgen_b200.camera import CameraInfo
+    from gsgen_b200.viewer import get_c2w, qvec2rotmat
+
+    ns = _defs("utils/transforms.py", ["qvec2rotmat"], {"np": np})
+    ns = _defs("utils/viewer/viser_viewer.py", ["get_c2w"], ns)
+    rng = np.random.default_rng(1)
+    for _ in range(10):
+        q = rng.standard_normal(4)
+        q /= np.linalg.norm(q)
+        pos = rng.standard_normal(3)
+        assert np.allclose(qvec2rotmat(q), ns["qvec2rotmat"](q), atol=1e-15)
+        cam = types.SimpleNamespace(wxyz=q, position=pos)
+        assert np.array_equal(get_c2w(q, pos), ns["get_c2w"](cam))
+    # from_fov_camera is a classmethod of the reference's CameraInfo: execute its body on a stand-in class
+    tree = ast.parse(open(os.path.join(REF, "utils/camera.py")).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "CameraInfo")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "from_fov_camera")
+    fn.decorator_list = []
+    ns2 = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "utils/camera.py", "exec"), ns2)
+    for fov, aspect, reso in ((0.9, 1.6, 512), (1.2, 0.75, 300), (0.5, 1.0, 64)):
+        want = ns2["from_fov_camera"](lambda *a: a, fov, aspect, reso, 0.01, 100.0)
+        got = CameraInfo.from_fov_camera(fov, aspect, reso, 0.01, 100.0)
+        assert (got.fx, got.fy, got.cx, got.cy, got.w, got.h, got.near_plane, got.far_plane) == want

@@ -230,7 +230,23 @@ def test_fused_view_fullsize_vs_reference_pipeline(ref_gs, oracle_mod, cfg):
                                                      c2w_cpu, C, cfg_o)
         return e, mx
 
-    classify_image_diff(out["rgb"], ro.view(H, W, 3), sh_margin, sh_exact, what=f"fused sh rgb C={C}", report=rows)
+    def sh_exact_own():
+        """the fp64 composite of the FUSED path's own per-Gaussian outputs: its mean2d / cov2d and ITS tile lists --
+        rebuilt on the CPU from its depth and its tile rectangles (integer work, bit-exact given the inputs; ties in
+        index order on both sides).  The lists matter: the fused front end and the torch op chain round the depth
+        differently in the last ulp, and two Gaussians of a tile whose depths are an ulp apart then composite in
+        swapped order (2M Gaussians at C5: a few hundred such pairs)."""
+        m2o, c2o = aux["mean2d"].detach()[mask].cpu().contiguous(), aux["cov2d"][mask].cpu().contiguous()
+        dpo = aux["depth"][mask].cpu().contiguous()
+        Do, tlo, bro = oracle_mod.tile_culling_aabb_count(m2o, c2o, 16, ocam_of(cam), 6.0)
+        assert Do == aux["N_with_dub"], (Do, aux["N_with_dub"])
+        ids_o, st_o, en_o = oracle_mod.tile_culling_aabb_start_end(tlo, bro, dpo, th, tw, Do)
+        e, _, mx = oracle_mod.composite_sh_fwd_exact(m2o, c2o, sh.cpu(), cpu[2], st_o, en_o, ids_o, cpu[6], c2w_cpu, C,
+                                                     cfg_o)
+        return e, mx
+
+    classify_image_diff(out["rgb"], ro.view(H, W, 3), sh_margin, sh_exact, what=f"fused sh rgb C={C}", report=rows,
+                        exact_self_fn=sh_exact_own)
     # ---- parameter gradients (north_star: xyz / scale / rot / opacity / SH within 1e-3 rel)
     full = lambda t, like: torch.zeros_like(like).index_put_((mask,), t)
     for a_, b_, n_ in ((mg.grad, mr.grad, "g_mean"), (qg.grad, qr.grad, "g_qvec"), (sg.grad, sr.grad, "g_svec"),

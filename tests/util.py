@@ -85,7 +85,7 @@ def ocam_of(cam):
 
 
 def classify_image_diff(ours, ref, margin_fn, exact_fn=None, atol=IMG_ATOL, what="image", flip_margin=2e-3,
-                        max_flip_frac=2e-3, report=None):
+                        max_flip_frac=2e-3, report=None, exact_self_fn=None):
     """Full-size parity of two fp32 implementations of the same composite (ours vs the reference extension).
 
     Every pixel with |ours - ref| > atol must be EXPLAINED, by one of
@@ -95,7 +95,13 @@ def classify_image_diff(ours, ref, margin_fn, exact_fn=None, atol=IMG_ATOL, what
                  fp64 arbiter (oracle.composite_sh_fwd_exact) -- i.e. OURS is within tolerance of the true value and
                  the remainder is the reference's own fp32 rounding (its `radial` formula, kernels.h:172-193, cancels
                  for thin Gaussians).
-    margin_fn() -> margin[H,W]; exact_fn() -> (exact[H,W,3] f64, margin_exact[H,W]) are only evaluated when needed.
+      (projection) only when the two sides composite DIFFERENT per-Gaussian inputs (the fused view against the reference
+                 pipeline: each side projects the Gaussians itself, in fp32, with its own operation order): the pixel is
+                 explained if OURS equals the fp64 composite of ITS OWN projected inputs (`exact_self_fn`) within atol, or
+                 sits on a 1/255 threshold of those inputs.  For sub-pixel, thin splats (C5) the conic amplifies an ulp of
+                 the projected covariance to ~1e-3 in a*G, enough to move a pair across the threshold although both
+                 projections agree to fp32 rounding (checked separately by the caller).
+    margin_fn() -> margin[H,W]; exact_fn() / exact_self_fn() -> (exact[H,W,3] f64, margin_exact[H,W]); all lazy.
     Returns a dict of counts (also appended to `report` when given)."""
     ours_c, ref_c = ours.detach().float().cpu(), ref.detach().float().cpu()
     assert ours_c.shape == ref_c.shape, (ours_c.shape, ref_c.shape)
@@ -125,6 +131,15 @@ def classify_image_diff(ours, ref, margin_fn, exact_fn=None, atol=IMG_ATOL, what
             res["ours_vs_exact_max_all"] = float(ex_pix.max())
             res["ref_vs_exact_max_all"] = float(ref_pix.max())
             rest = rest & ~rounding
+        if int(rest.sum()) and exact_self_fn is not None:
+            ex_s, margin_s = exact_self_fn()
+            es = (ours_c.double() - ex_s.reshape(ours_c.shape)).abs()
+            es_pix = es.amax(dim=-1) if es.dim() == 3 else es
+            proj = rest & ((es_pix <= atol) | (margin_s.reshape(epix.shape) < flip_margin))
+            res["projection_explained"] = int(proj.sum())
+            res["ours_vs_exact_of_own_inputs_max"] = float(es_pix[proj].max()) if int(proj.sum()) else 0.0
+            res["ours_vs_exact_of_own_inputs_max_all"] = float(es_pix.max())
+            rest = rest & ~proj
         res["flip_explained"] = int(flip.sum())
         res["flip_max_err"] = float(epix[flip].max()) if int(flip.sum()) else 0.0
         res["unexplained"] = int(rest.sum())
