@@ -155,12 +155,15 @@ __device__ __noinline__ void flush_direct(const FlushDst a, const float* my_t, c
 #ifndef GSB_BWDSH_PREFETCH
 #define GSB_BWDSH_PREFETCH 0  // 1: hit-loop software pipeline (next record fetched while the current one is evaluated); measured round 2: 1.028 ms with, 1.013 ms without (C3)
 #endif
+#ifndef GSB_BWDSH_NW
+#define GSB_BWDSH_NW 8  // warps per CTA: 8 = one CTA per 16x16 tile; 4 = two CTAs per tile (16x8 pixels each, both walk
+#endif                  // the tile's list; fewer warps wait at the per-batch barrier and a half tile terminates earlier)
 #ifndef GSB_BWDSH_MINBLOCKS
-#define GSB_BWDSH_MINBLOCKS 3
+#define GSB_BWDSH_MINBLOCKS (GSB_BWDSH_NW == 8 ? 3 : 6)
 #endif
 
 template <int C, bool FUSED, int B>
-__global__ void __launch_bounds__(kCtaThreads, GSB_BWDSH_MINBLOCKS)
+__global__ void __launch_bounds__(GSB_BWDSH_NW * 32, GSB_BWDSH_MINBLOCKS)
 k_composite_bwd_sh(const CompositeArgs a) {
   using L = StageLayout<PAY_SH, C, B, true>;
   using PT = PayTraits<PAY_SH, C>;
@@ -170,12 +173,12 @@ k_composite_bwd_sh(const CompositeArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t s_bar[2];
 
-  float* s_tbuf = reinterpret_cast<float*>(smem + 2 * L::kBytes);  // [8 warps][kWarpFloats]
+  float* s_tbuf = reinterpret_cast<float*>(smem + 2 * L::kBytes);  // [GSB_BWDSH_NW warps][kWarpFloats]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y;
   const int tile = tile_y * a.tiles_w + tile_x;
-  const PixelGeom pg = pixel_geom(a, tile_x, tile_y, warp, lane);
+  const PixelGeom pg = pixel_geom(a, tile_x, tile_y, warp + (int)blockIdx.z * GSB_BWDSH_NW, lane);
   const int pix = pg.gy * a.W + pg.gx;
 
   const int s0 = a.start[tile];
@@ -355,11 +358,13 @@ static int launch_one_sh(const CompositeArgs& a, cudaStream_t st) {
   using L = StageLayout<PAY_SH, C, B, true>;
   using ST = ShBwdTraits<C>;
   static_assert(B <= 256, "entry indices are packed in 8 bits");
-  const size_t smem = 2 * (size_t)L::kBytes + (size_t)8 * ST::kWarpFloats * 4;
+  static_assert(GSB_BWDSH_NW == 8 || GSB_BWDSH_NW == 4, "8 warps = whole tile, 4 = half tile");
+  static_assert(B <= GSB_BWDSH_NW * 32, "one thread stages one list entry");
+  const size_t smem = 2 * (size_t)L::kBytes + (size_t)GSB_BWDSH_NW * ST::kWarpFloats * 4;
   auto kern = k_composite_bwd_sh<C, FUSED, B>;
   GSB_CUDA(ensure_max_dyn_smem(reinterpret_cast<const void*>(kern), (int)smem, a.device));
-  dim3 grid(a.tiles_w, a.tiles_h, 1);
-  kern<<<grid, kCtaThreads, smem, st>>>(a);
+  dim3 grid(a.tiles_w, a.tiles_h, 8 / GSB_BWDSH_NW);
+  kern<<<grid, GSB_BWDSH_NW * 32, smem, st>>>(a);
   GSB_LAUNCH_CHECK();
   return GSB200_OK;
 }

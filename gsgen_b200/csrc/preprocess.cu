@@ -220,7 +220,7 @@ k_preprocess(uint32_t N, const float* __restrict__ mean, const float* __restrict
 // fused back end: gradient records of the composite backward -> parameter gradients (all written).
 //   ggeom[i] = {gmx, gmy, gxx, gxy | gyy, galpha, gdepth, -}   gpay[i] = {gr, gg, gb, -}
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 k_project_bwd_fused(uint32_t N, const float* __restrict__ mean, const float* __restrict__ qvec,
                     const float* __restrict__ svec, const float* __restrict__ alpha,
                     const float* __restrict__ color, int act, const uint8_t* __restrict__ mask, Camera cam,
@@ -232,6 +232,20 @@ k_project_bwd_fused(uint32_t N, const float* __restrict__ mean, const float* __r
   float gx[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f};
   float ga = 0.f, gcol[3] = {0.f, 0.f, 0.f}, gm2[2] = {0.f, 0.f};
   const bool vis = mask[i] != 0;
+  // accumulate mode: the running gradients are fetched together with the inputs (ONE round of HBM latency instead of
+  // two: measured round 2, this kernel was latency bound -- 38 % issue slots, long-scoreboard stall 12.4 per issue)
+  float om[3] = {0.f, 0.f, 0.f}, os[3] = {0.f, 0.f, 0.f}, oa = 0.f, oc[3] = {0.f, 0.f, 0.f};
+  float4 oq = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (accumulate && vis) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { om[k] = g_mean[3 * i + k]; os[k] = g_svec[3 * i + k]; }
+    oq = reinterpret_cast<const float4*>(g_qvec)[i];
+    oa = g_alpha[i];
+    if (g_color) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) oc[k] = g_color[3 * i + k];
+    }
+  }
   if (vis) {
     float4 g0 = ggeom[2 * i], g1 = ggeom[2 * i + 1];
     float x[3] = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2]};
@@ -259,13 +273,12 @@ k_project_bwd_fused(uint32_t N, const float* __restrict__ mean, const float* __r
   if (accumulate) {  // += into the caller's running gradient (e.g. the flat all-reduce buffer); culled: no traffic
     if (!vis) return;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { g_mean[3 * i + k] += gx[k]; g_svec[3 * i + k] += gs[k]; }
-    float4 o = reinterpret_cast<float4*>(g_qvec)[i];
-    reinterpret_cast<float4*>(g_qvec)[i] = make_float4(o.x + gq[0], o.y + gq[1], o.z + gq[2], o.w + gq[3]);
-    g_alpha[i] += ga;
+    for (int k = 0; k < 3; ++k) { g_mean[3 * i + k] = om[k] + gx[k]; g_svec[3 * i + k] = os[k] + gs[k]; }
+    reinterpret_cast<float4*>(g_qvec)[i] = make_float4(oq.x + gq[0], oq.y + gq[1], oq.z + gq[2], oq.w + gq[3]);
+    g_alpha[i] = oa + ga;
     if (g_color) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) g_color[3 * i + k] += gcol[k];
+      for (int k = 0; k < 3; ++k) g_color[3 * i + k] = oc[k] + gcol[k];
     }
     return;
   }

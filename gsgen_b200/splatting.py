@@ -41,6 +41,31 @@ def _get(cfg, key, default=None):
     return getattr(cfg, key, default)
 
 
+def scheduled_value(value, step, max_steps=None) -> float:
+    """utils/misc.py:218-250 `C(value, step)`: a number, or [start_step, start_value, end_value, end_step] (3 entries:
+    start_step = 0) linearly interpolated and clamped; a FLOAT end_step means a fraction of max_steps."""
+    if isinstance(value, (int, float)):
+        return value
+    value = list(value)
+    if len(value) == 3:
+        value = [0] + value
+    if len(value) != 4:
+        raise TypeError(f"Scalar specification only supports a number or a list of 3 / 4 entries, got {value}")
+    start_step, start_value, end_value, end_step = value
+    if isinstance(end_step, int):
+        current = step
+    else:
+        if max_steps is None:
+            raise ValueError("max_steps must be specified when using float step")
+        current = end_step * max_steps
+    return start_value + (end_value - start_value) * max(min(1.0, (current - start_step) / (end_step - start_step)), 0.0)
+
+
+def _scalar(writer, tag, value, step):
+    if writer is not None and hasattr(writer, "add_scalar"):
+        writer.add_scalar(tag, value.item() if torch.is_tensor(value) else value, step)
+
+
 def stack_dicts(dicts: Sequence[Dict[str, torch.Tensor]]) -> Dict[str, torch.Tensor]:
     """utils/misc.py:180-184"""
     return {k: torch.stack([d[k] for d in dicts], dim=0) for k in dicts[0].keys()}
@@ -181,6 +206,105 @@ class GaussianSplattingRenderer:
 
     def prune(self, step: int):
         return self.store.prune_step(step, _get(self.cfg, "prune", {"enabled": False}))
+
+    # ---- auxiliary losses (gs/gaussian_splatting.py:950-1122) ----------------------------------------------
+    def _penalty_cfg(self, key):
+        pen = _get(self.cfg, "penalty", None)
+        return None if pen is None else _get(pen, key, None)
+
+    def alpha_penalty_loss(self, step, writer=None):
+        """:950-970 -- "uniform_l1" | "uniform_l2" | "center_weighted" (the shipped configs, conf/renderer/*.yaml:50-53)"""
+        c = self._penalty_cfg("alpha")
+        w = scheduled_value(_get(c, "value", 0.0), step) if c is not None else 0.0
+        if not w > 0.0:
+            return torch.zeros_like(self.alpha[0], requires_grad=False)
+        kind = _get(c, "type")
+        if kind == "uniform_l1":
+            pen = torch.mean(self.alpha)
+        elif kind == "uniform_l2":
+            pen = torch.mean(self.alpha ** 2)
+        elif kind == "center_weighted":
+            pen = torch.mean(self.mean.detach().norm(dim=-1) * self.alpha)
+        else:
+            raise ValueError(f"Unknown alpha penalty type: {kind}")
+        _scalar(writer, "auxiliary/alpha_penalty", pen, step)
+        _scalar(writer, "auxiliary/alpha_penalty_weight", w, step)
+        return w * pen
+
+    def mean_penalty_loss(self, step, writer=None):
+        """:972-999"""
+        c = self._penalty_cfg("mean")
+        w = scheduled_value(_get(c, "value", 0.0), step) if c is not None else 0.0
+        if not w > 0.0:
+            return torch.zeros_like(self.alpha[0], requires_grad=False)
+        kind, r = _get(c, "type"), self.mean.norm(dim=-1)
+        if kind == "uniform_l1":
+            pen = torch.mean(r)
+        elif kind == "uniform_l2":
+            pen = torch.mean(r ** 2)
+        elif kind == "weighted_l1":
+            pen = torch.mean(r.detach() * r)
+        elif kind == "weighted_l2":
+            pen = torch.mean(r.detach() ** 2 * r ** 2)
+        else:
+            raise ValueError(f"Unknown mean penalty type: {kind}")
+        _scalar(writer, "auxiliary/mean_penalty", pen, step)
+        _scalar(writer, "auxiliary/mean_penalty_weight", w, step)
+        return w * pen
+
+    def scale_penalty_loss(self, step, writer=None):
+        """:1001-1013 (total volume prod(svec).sum())"""
+        c = self._penalty_cfg("scale")
+        w = scheduled_value(_get(c, "value", 0.0), step) if c is not None else 0.0
+        if not w:
+            return torch.zeros_like(self.alpha[0], requires_grad=False)
+        volume = self.svec.prod(dim=-1).sum()
+        _scalar(writer, "auxiliary/scale_penalty", volume, step)
+        _scalar(writer, "auxiliary/scale_penalty_weight", w, step)
+        return w * volume
+
+    def auxiliary_loss(self, step, writer=None):
+        """:1115-1122: the sum of `<key>_penalty_loss` over cfg.penalty.  The K-nearest-neighbour penalties (NN, compat)
+        and the PBR ones (normal, specular) belong to subsystems outside the hot path and raise here."""
+        loss = 0.0
+        pen = _get(self.cfg, "penalty", None) or {}
+        for key in (pen.keys() if hasattr(pen, "keys") else vars(pen)):
+            fn = getattr(self, f"{key}_penalty_loss", None)
+            if fn is None:
+                raise NotImplementedError(f"penalty '{key}' is not part of the rasterizer hot path")
+            loss = loss + fn(step, writer)
+        if torch.is_tensor(loss):
+            _scalar(writer, "auxiliary/total", loss, step)
+        return loss
+
+    # ---- logging (gs/gaussian_splatting.py:1477-1565) --------------------------------------------------------
+    @torch.no_grad()
+    def log(self, writer, step):
+        """scalars / histograms the reference writes: parameter bounds, gradient bounds, learning rates, densification
+        statistics.  `writer`: anything with add_scalar / add_histogram (tensorboard SummaryWriter)."""
+        _scalar(writer, "renderer/num_gaussians", self.N, step)
+        st = self.store
+        for field in FIELDS:
+            v = getattr(self, field)
+            _scalar(writer, f"renderer/{field}/min", v.abs().min(), step)
+            _scalar(writer, f"renderer/{field}/max", v.abs().max(), step)
+            _scalar(writer, f"renderer/{field}/mean", v.mean(), step)
+            g = st.grad_views[field]
+            _scalar(writer, f"renderer/{field}/grad_min", g.abs().min(), step)
+            _scalar(writer, f"renderer/{field}/grad_max", g.abs().max(), step)
+        if self.optimizer is not None:
+            for name, lr in self.optimizer.lr_at(self.step).items():
+                _scalar(writer, f"lr/{name}", lr, step)
+        if hasattr(writer, "add_histogram"):
+            writer.add_histogram("hists/mean", self.mean.norm(dim=-1).cpu().numpy(), step)
+            writer.add_histogram("hists/svec_min", self.svec.min(dim=-1)[0].cpu().numpy(), step)
+            writer.add_histogram("hists/svec_max", self.svec.max(dim=-1)[0].cpu().numpy(), step)
+            writer.add_histogram("hists/alpha", self.alpha.cpu().numpy(), step)
+            writer.add_histogram("hists/grad_mean", st.grad_views["mean"].norm(dim=-1).cpu().numpy(), step)
+            writer.add_histogram("hists/max_radii2d", st.max_radii2d.cpu().numpy(), step)
+            if _get(_get(self.cfg, "densify", {}), "enabled", False):
+                writer.add_histogram("hists/grad_mean2d", st.mean_2d_grad_accum.cpu().numpy(), step)
+                writer.add_histogram("hists/cnt", st.cnt.cpu().numpy(), step)
 
     # ---- checkpoints ---------------------------------------------------------------------------------------
     def get_params_for_save(self):

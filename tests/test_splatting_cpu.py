@@ -134,3 +134,77 @@ def test_trainer_call_sequence(gold, oracle_mod, tmp_path):
     r2 = GaussianSplattingRenderer.load({}, path, device="cpu", render_fn=_oracle_render_fn(oracle_mod))
     assert r2.N == r.N and torch.equal(r2.mean.detach(), r.mean.detach())
     assert torch.allclose(r2.svec.detach(), r.svec.detach())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference not mounted")
+def test_auxiliary_losses_match_the_reference_methods(gold, oracle_mod):
+    """alpha / mean / scale penalties and auxiliary_loss against the reference's own method definitions
+    (gs/gaussian_splatting.py:950-1013, :1115-1122) and its schedule helper C (utils/misc.py:218-250), executed with
+    `ast` on a stand-in object."""
+    import ast
+    import types
+
+    from gsgen_b200.splatting import scheduled_value
+
+    def defs(path, names, ns, in_class=None):
+        tree = ast.parse(open(os.path.join("/root/reference", path)).read())
+        body = tree.body
+        if in_class:
+            body = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == in_class).body
+        for node in body:
+            if isinstance(node, ast.FunctionDef) and node.name in names:
+                node.returns, node.decorator_list = None, []
+                for a in node.args.args:
+                    a.annotation = None
+                exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+        return ns
+
+    ns = defs("utils/misc.py", ["C"], {"np": np, "Any": object, "to_primitive": lambda v: list(v)})
+    for spec, step in ((3.5, 10), ([0, 1.0, 5.0, 100], 25), ([10, 2.0, 0.5, 60], 5), ([1.0, 3.0, 50], 20)):
+        assert scheduled_value(spec, step) == pytest.approx(ns["C"](spec, step, None))
+    names = ["alpha_penalty_loss", "mean_penalty_loss", "scale_penalty_loss", "auxiliary_loss"]
+    ns = defs("gs/gaussian_splatting.py", names, dict(ns, torch=torch), in_class="GaussianSplattingRenderer")
+
+    class W:
+        def __init__(self):
+            self.s = {}
+
+        def add_scalar(self, k, v, step=None):
+            self.s[k] = float(v)
+
+    NS = types.SimpleNamespace
+    for kind_a, kind_m in (("center_weighted", "weighted_l2"), ("uniform_l2", "uniform_l1")):
+        pen = {"alpha": {"type": kind_a, "value": [0, 10.0, 100.0, 200]}, "mean": {"type": kind_m, "value": 0.5},
+               "scale": {"value": 2.0}}
+        r, cam = _renderer(gold, "a", oracle_mod, cfg={"penalty": pen})
+        step = 50
+        w_ours, w_ref = W(), W()
+        ours = r.auxiliary_loss(step, w_ours)
+        ours.backward()
+        g_ours = {k: r.store.grad_views[k].clone() for k in ("mean", "svec", "alpha")}
+        # the reference's methods on a stand-in that exposes the same activated views of fresh leaves
+        leaves = {k: r.store.params[k].detach().clone().requires_grad_() for k in ("mean", "svec", "alpha")}
+        ref_self = NS(cfg=NS(penalty=NS(alpha=NS(**pen["alpha"]), mean=NS(**pen["mean"]), scale=NS(**pen["scale"]))),
+                      mean=leaves["mean"], alpha=torch.sigmoid(leaves["alpha"]), svec=torch.exp(leaves["svec"]))
+        ref_self.cfg.penalty.__iter__ = None
+        for n in names[:3]:
+            setattr(ref_self, n, types.MethodType(ns[n], ref_self))
+
+        class Pen(dict):  # `for key in self.cfg.penalty` + attribute access
+            __getattr__ = dict.__getitem__
+
+        ref_self.cfg = NS(penalty=Pen({k: NS(**v) for k, v in pen.items()}))
+        ref = ns["auxiliary_loss"](ref_self, step, w_ref)
+        ref.backward()
+        assert float(ours) == pytest.approx(float(ref), rel=1e-6)
+        for k in g_ours:
+            assert torch.allclose(g_ours[k], leaves[k].grad, rtol=1e-5, atol=1e-9), k
+        assert w_ours.s.keys() == w_ref.s.keys()
+        for k in w_ref.s:
+            assert w_ours.s[k] == pytest.approx(w_ref.s[k], rel=1e-6), k
+    # log(): smoke (tags the reference writes)
+    w = W()
+    w.h = {}
+    w.add_histogram = lambda k, v, step=None: w.h.__setitem__(k, len(v))
+    r.log(w, 3)
+    assert "renderer/num_gaussians" in w.s and "renderer/alpha/grad_max" in w.s and "hists/max_radii2d" in w.h
