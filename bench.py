@@ -704,6 +704,15 @@ def run_ours(args):
     runs = timed_loops(args, step, barrier, world, dev, N_LOOPS, sampler, rank)
     all_runs_ms = [r[0] for r in runs]
     ms_max, mark0, mark1 = sorted(runs, key=lambda r: r[0])[N_LOOPS // 2]
+    if w.async_count:  # no view of the timed loops may have been truncated: the blocking check of every context
+        from gsgen_b200._lib import TileListOverflow
+        from gsgen_b200.rasterizer import view_stats
+
+        for s_ in w.slot_of.values():
+            try:
+                view_stats(dev, s_)
+            except TileListOverflow:
+                w.overflows += 1
     ar_ms = time_allreduce(w, barrier, world, dev)
     # ---- the same K steps again with every stage bracketed by CUDA events on the launching stream
     # (gsb200_ctx_set_profiling).  Kept out of the headline loop because the bracketing perturbs it (reported).

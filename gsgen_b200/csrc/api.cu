@@ -99,23 +99,56 @@ static int next_evset(gsb200_ctx::EvSet** sets, int* cap, int* used, gsb200_ctx:
     if (set) GSB_CUDA(cudaEventRecord((set)->e[k], st));     \
   } while (0)
 
-// Asynchronous-count mode: the host consumes the duplicate count of the context's last forward (waits for the 16-byte
-// copy enqueued right behind the front-end kernel -- long done by the time anybody asks).  Returns GSB200_ERR_OVERFLOW
-// when the tile lists did not fit the capacity the sort covered: that view's images / saved state are truncated.
-static int resolve_total(gsb200_ctx* ctx) {
-  if (!ctx->pending_total) return GSB200_OK;
-  int64_t tot[2] = {0, 0};
-  int rc = wait_total(ctx, tot);
-  if (rc) return rc;
-  ctx->pending_total = 0;
-  ctx->D = tot[0];
-  ctx->N_visible = ctx->h_total[1];
-  if (tot[0] > ctx->dup_seen) ctx->dup_seen = tot[0];
-  if (ctx->profiling) ctx->sum_dup += tot[0];
-  GSB_CHECK(tot[0] <= ctx->dup_capacity, GSB200_ERR_OVERFLOW,
-            "asynchronous-count mode: the view expands to %lld duplicates but the tile sort covered %lld (capacity from "
-            "earlier views): its lists are truncated -- render the view again (the capacity has been raised)",
-            (long long)tot[0], (long long)ctx->dup_capacity);
+// Asynchronous-count mode.  A forward enqueues a 16-byte copy of its counters into a pinned ring slot and records an
+// event; nobody waits for it.  poll_counts consumes the completed slots in order -- non-blocking (cudaEventQuery) from
+// the forward / backward paths, blocking from gsb200_view_stats and the synchronous ops -- learns the capacity from
+// them and remembers the first view whose lists did not fit; report_overflow turns that into GSB200_ERR_OVERFLOW once.
+static int push_count(gsb200_ctx* ctx, cudaStream_t st);
+static int poll_counts(gsb200_ctx* ctx, bool block) {
+  while (ctx->ring_tail < ctx->ring_head) {
+    const int slot = (int)(ctx->ring_tail % gsb200_ctx::kRing);
+    if (block) {
+      GSB_CUDA(cudaEventSynchronize(ctx->ev_ring[slot]));
+    } else {
+      cudaError_t q = cudaEventQuery(ctx->ev_ring[slot]);
+      if (q == cudaErrorNotReady) break;
+      GSB_CUDA(q);
+    }
+    const int64_t dup = ctx->h_ring[2 * slot], vis = ctx->h_ring[2 * slot + 1];
+    if (dup > ctx->dup_seen) ctx->dup_seen = dup;
+    if (ctx->profiling) ctx->sum_dup += dup;
+    if (ctx->ring_gen[slot] == ctx->generation) { ctx->D = dup; ctx->N_visible = vis; }
+    if (dup > ctx->ring_cap[slot] && ctx->overflow_gen == 0) {
+      ctx->overflow_gen = ctx->ring_gen[slot]; ctx->overflow_dup = dup; ctx->overflow_cap = ctx->ring_cap[slot];
+    }
+    ++ctx->ring_tail;
+  }
+  return GSB200_OK;
+}
+static int report_overflow(gsb200_ctx* ctx) {
+  if (ctx->overflow_gen == 0) return GSB200_OK;
+  const long long g = ctx->overflow_gen, d = ctx->overflow_dup, c = ctx->overflow_cap;
+  ctx->overflow_gen = 0;
+  set_error("asynchronous-count mode: the forward with generation %lld expands to %lld duplicates but its tile sort "
+            "covered %lld (capacity learnt from earlier views): its tile lists were truncated -- render that view "
+            "again (the capacity has been raised)", g, d, c);
+  return GSB200_ERR_OVERFLOW;
+}
+static int push_count(gsb200_ctx* ctx, cudaStream_t st) {
+  if (!ctx->h_ring) GSB_CUDA(cudaHostAlloc((void**)&ctx->h_ring, gsb200_ctx::kRing * 2 * sizeof(int64_t), cudaHostAllocDefault));
+  if (ctx->ring_head - ctx->ring_tail == (unsigned long long)gsb200_ctx::kRing) {  // ring full: consume the oldest
+    const int old = (int)(ctx->ring_tail % gsb200_ctx::kRing);
+    GSB_CUDA(cudaEventSynchronize(ctx->ev_ring[old]));
+    int rc = poll_counts(ctx, false);
+    if (rc) return rc;
+  }
+  const int slot = (int)(ctx->ring_head % gsb200_ctx::kRing);
+  if (!ctx->ev_ring[slot]) GSB_CUDA(cudaEventCreateWithFlags(&ctx->ev_ring[slot], cudaEventDisableTiming));
+  GSB_CUDA(cudaMemcpyAsync(ctx->h_ring + 2 * slot, ctx->d_total.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  GSB_CUDA(cudaEventRecord(ctx->ev_ring[slot], st));
+  ctx->ring_gen[slot] = ctx->generation;
+  ctx->ring_cap[slot] = ctx->dup_capacity;
+  ++ctx->ring_head;
   return GSB200_OK;
 }
 
@@ -142,6 +175,7 @@ int gsb200_ctx_create(int device, gsb200_ctx** out) {
   // tuning / A-B defaults from the environment (the options themselves: gsb200_ctx_set_option)
   if (const char* e = getenv("GSB200_BWD_SH_VARIANT")) c->bwd_sh_variant = atoi(e);
   if (const char* e = getenv("GSB200_ASYNC_COUNT")) c->async_count = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("GSB200_FWD_SH_VARIANT")) c->fwd_sh_variant = atoi(e) ? 1 : 0;
   *out = c;
   return GSB200_OK;
 }
@@ -154,6 +188,8 @@ int gsb200_ctx_destroy(gsb200_ctx* c) {
                       &c->d_overflow, &c->d_small, &c->dkeys[0], &c->dkeys[1], &c->perm[0], &c->perm[1], &c->d_stats};
   for (auto* b : bufs) b->release();
   if (c->h_total) cudaFreeHost(c->h_total);
+  if (c->h_ring) cudaFreeHost(c->h_ring);
+  for (auto& e : c->ev_ring) if (e) cudaEventDestroy(e);
   if (c->ev_total) cudaEventDestroy(c->ev_total);
   delete c;
   return GSB200_OK;
@@ -173,7 +209,7 @@ int gsb200_tile_culling_aabb_start_end(gsb200_ctx* ctx, const int32_t* tl, const
   int rc;
   if ((rc = set_device(ctx))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (ctx->pending_total) { int r2 = resolve_total(ctx); if (r2 && r2 != GSB200_ERR_OVERFLOW) return r2; }
+  if ((rc = poll_counts(ctx, true))) return rc;
   GSB_CHECK(start && end, GSB200_ERR_INVALID, "tile_culling_aabb_start_end: null start/end");
   GSB_CHECK(tw <= 65535 && th <= 65535, GSB200_ERR_UNSUPPORTED, "tile grid too large");
   if (N > 0) {
@@ -290,6 +326,7 @@ int gsb200_tile_based_vol_rendering_sh(
   fill_common(a, ctx, start, end, ids, topleft, th, tw, psx, psy, H, W, thresh);
   a.sh = sh; a.c9_ptr = c2w; a.bg_rgb = bg_rgb;
   a.out = out;
+  if (C >= 3 && ctx->fwd_sh_variant == 1) return launch_composite_fwd_sh2((int)C, a, st);
   return launch_composite_fwd(PAY_SH, (int)C, false, a, st);
 }
 
@@ -346,7 +383,7 @@ int gsb200_tile_culling_aabb_count(gsb200_ctx* ctx, const float* mean2d, const f
   if ((rc = set_device(ctx))) return rc;
   GSB_CHECK(tile_size >= 1, GSB200_ERR_INVALID, "tile_size must be positive");
   GSB_CHECK(h_total != nullptr, GSB200_ERR_INVALID, "null h_N_with_dub");
-  if (ctx->pending_total) { int r2 = resolve_total(ctx); if (r2 && r2 != GSB200_ERR_OVERFLOW) return r2; }
+  if ((rc = poll_counts(ctx, true))) return rc;
   *h_total = 0;
   if (N == 0) return GSB200_OK;
   GSB_CHECK(mean2d && cov2d && tl && br, GSB200_ERR_INVALID, "tile_culling_aabb_count: null tensor");
@@ -384,13 +421,17 @@ int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb
   int64_t D = 0;
   gsb200_ctx::EvSet* ev = nullptr;
   if (ctx->profiling && (rc = next_evset(&ctx->fwd_sets, &ctx->fwd_cap, &ctx->fwd_used, &ev))) return rc;
-  // a count still in flight from the previous forward on this context is consumed first (h_total is reused); an
-  // overflow of THAT view is its own backward's / view_stats' business -- here only the capacity learns from it
-  if (ctx->pending_total) { int rc2 = resolve_total(ctx); if (rc2 && rc2 != GSB200_ERR_OVERFLOW) return rc2; }
+  // counts of earlier asynchronous forwards that have arrived are consumed (non-blocking): the capacity learns from
+  // them; an overflow among them is reported here, before this view is rendered on top of a stale capacity
+  if ((rc = poll_counts(ctx, false))) return rc;
+  if ((rc = report_overflow(ctx))) return rc;
   if (ctx->seen_N != N || ctx->seen_W != cam.W || ctx->seen_H != cam.H) {
+    if ((rc = poll_counts(ctx, true))) return rc;  // (counts of the previous shape must not teach the new one)
+    ctx->overflow_gen = 0;
     ctx->seen_N = N; ctx->seen_W = cam.W; ctx->seen_H = cam.H; ctx->dup_seen = 0;
   }
   const bool padded = ctx->async_count && ctx->dup_seen > 0 && N > 0;
+  ctx->generation = ++g_generation;
   GSB_EV(ev, 0, st);
   if (N > 0) {
     GSB_CHECK(in->mean && in->qvec && in->svec && in->alpha, GSB200_ERR_INVALID, "render_forward: null parameter tensor");
@@ -408,18 +449,21 @@ int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb
                                 ctx->count.as<int32_t>(), ctx->dkeys[0].as<uint32_t>(), ctx->perm[0].as<int32_t>(),
                                 ctx->d_total.as<unsigned long long>(), st)))
       return rc;
-    if ((rc = request_total(ctx, st))) return rc;
-    GSB_EV(ev, 1, st);
-    if ((rc = sort_depths_and_scan(ctx, N, out->depthg, st, /*keys_ready=*/true))) return rc;  // GPU keeps working ...
     if (padded) {
-      // ... and the host does not wait at all: the sort covers a capacity learnt from earlier views of this context
-      // (largest count seen + 1/8), keys beyond the device-side count are padding; the exact count is consumed by
-      // gsb200_render_backward / gsb200_view_stats, which reject the view if it did not fit.
-      ctx->pending_total = 1;
+      // the host does not wait at all: the sort covers a capacity learnt from earlier views of this context (largest
+      // count seen + 1/8), keys beyond the device-side count are padding; the exact count travels to a pinned ring
+      // slot and is consumed by a later poll (next forward / backward on this context, or gsb200_view_stats)
       ctx->D = -1;
+      ctx->N_visible = -1;
       ctx->dup_capacity = ctx->dup_seen + ctx->dup_seen / 8 + 4096;
       D = -1;
+      if ((rc = push_count(ctx, st))) return rc;
     } else {
+      if ((rc = request_total(ctx, st))) return rc;
+    }
+    GSB_EV(ev, 1, st);
+    if ((rc = sort_depths_and_scan(ctx, N, out->depthg, st, /*keys_ready=*/true))) return rc;  // GPU keeps working ...
+    if (!padded) {
       int64_t tot[2] = {0, 0};
       if ((rc = wait_total(ctx, tot))) return rc;  // ... while the host waits only for the 16-byte counters (the one
                                                    // host wait of the view; the reference blocks twice + 5 cudaMalloc/Free)
@@ -437,7 +481,6 @@ int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb
   if ((rc = bin_and_sort(ctx, N, padded ? ctx->dup_capacity : D, cam.tiles_h, cam.tiles_w, nullptr,
                          ctx->start.as<int32_t>(), ctx->end.as<int32_t>(), st, padded)))
     return rc;
-  ctx->generation = ++g_generation;
   if (out->h_generation) *out->h_generation = ctx->generation;
   GSB_EV(ev, 3, st);
   ctx->N = N; ctx->cam = cam; ctx->mode = is_sh ? PAY_SH : PAY_RGB; ctx->C = is_sh ? in->C : 1;
@@ -466,7 +509,11 @@ int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb
   a.out = out->rgb; a.T = out->T;
   a.depth = out->depth; a.opacity = out->opacity; a.z2 = out->z2;
   a.stats = ctx->profiling ? ctx->d_stats.as<unsigned long long>() : nullptr;
-  if ((rc = launch_composite_fwd(is_sh ? PAY_SH : PAY_RGB, is_sh ? in->C : 1, extras, a, st))) return rc;
+  if (is_sh && in->C >= 3 && ctx->fwd_sh_variant == 1) {
+    if ((rc = launch_composite_fwd_sh2(in->C, a, st))) return rc;
+  } else if ((rc = launch_composite_fwd(is_sh ? PAY_SH : PAY_RGB, is_sh ? in->C : 1, extras, a, st))) {
+    return rc;
+  }
   GSB_EV(ev, 4, st);
   return GSB200_OK;
 }
@@ -483,7 +530,9 @@ int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* camin, const gs
             "render_backward: the context was overwritten by a later forward (this view is generation %lld, the context "
             "holds %lld): give every in-flight view its own context",
             (long long)g->generation, (long long)ctx->generation);
-  if ((rc = resolve_total(ctx))) return rc;  // asynchronous-count mode: rejects a view whose lists were truncated
+  // asynchronous-count mode: consume the counts that have arrived (no wait) and reject a view found truncated
+  if ((rc = poll_counts(ctx, false))) return rc;
+  if ((rc = report_overflow(ctx))) return rc;
   GSB_CHECK(in->N == 0 || ((reinterpret_cast<uintptr_t>(in->qvec) | reinterpret_cast<uintptr_t>(g->g_qvec)) & 15) == 0,
             GSB200_ERR_INVALID, "render_backward: qvec and g_qvec must be 16-byte aligned (float4 accesses)");
   GSB_CHECK(g->rgb && g->mask && g->g_mean && g->g_qvec && g->g_svec && g->g_alpha, GSB200_ERR_INVALID,
@@ -527,7 +576,7 @@ int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* camin, const gs
   a.gpay = ctx->gpay.as<float>();
   a.grad_pay = g->g_sh;
   a.g_bg = g->g_bg;
-  if (ctx->D > 0 || g->g_bg) {
+  if (ctx->D != 0 || g->g_bg) {  // (D < 0: count not consumed yet in asynchronous-count mode)
     if (is_sh && in->C >= 2 && ctx->bwd_sh_variant == 0) {
       if ((rc = launch_composite_bwd_sh(in->C, true, a, st))) return rc;
     } else if ((rc = launch_composite_bwd(is_sh ? PAY_SH : PAY_RGB, is_sh ? in->C : 1, extras, true, a, st))) {
@@ -627,8 +676,8 @@ int gsb200_view_stats(gsb200_ctx* ctx, int64_t* h_out, gsb200_stream stream) {
   GSB_CHECK(h_out, GSB200_ERR_INVALID, "null h_out");
   GSB_CHECK(ctx->generation != 0, GSB200_ERR_INVALID, "view_stats: no forward has run on this context");
   cudaStream_t st = (cudaStream_t)stream;
-  const int rc_count = resolve_total(ctx);
-  if (rc_count && rc_count != GSB200_ERR_OVERFLOW) return rc_count;
+  if ((rc = poll_counts(ctx, true))) return rc;  // blocks until every count in flight has arrived
+  const int rc_count = report_overflow(ctx);
   const uint32_t T = (uint32_t)ctx->cam.tiles_w * (uint32_t)ctx->cam.tiles_h;
   if ((rc = ctx->d_overflow.reserve(2 * sizeof(int32_t)))) return rc;
   int32_t* d_max = ctx->d_overflow.as<int32_t>() + 1;
@@ -651,6 +700,10 @@ int gsb200_ctx_set_option(gsb200_ctx* ctx, int option, int64_t value) {
       return GSB200_OK;
     case GSB200_OPT_ASYNC_COUNT:
       ctx->async_count = value ? 1 : 0;
+      return GSB200_OK;
+    case GSB200_OPT_FWD_SH_VARIANT:
+      GSB_CHECK(value == 0 || value == 1, GSB200_ERR_INVALID, "fwd_sh_variant must be 0 or 1");
+      ctx->fwd_sh_variant = (int)value;
       return GSB200_OK;
     default:
       break;

@@ -84,13 +84,22 @@ struct gsb200_ctx {
   // options (gsb200_ctx_set_option)
   int bwd_sh_variant = 0;      // 0: direct vector-reduction flush (composite_bwd_sh.cu); 1: round-1 shared accumulator
   int async_count = 0;         // 1: render_forward does not wait for N_with_dub (capacity from earlier views)
+  int fwd_sh_variant = 0;      // 0: one pixel per thread (composite_fwd.cu); 1: two pixels per thread (composite_fwd2.cu)
   // saved view state
   uint32_t N = 0;
   int64_t D = 0;               // exact duplicate count of the last view, -1 while unresolved (async-count mode)
   int64_t dup_capacity = 0;    // async-count mode: entries the tile sort covered (>= D unless overflow)
   int64_t dup_seen = 0;        // largest N_with_dub this context has seen for the current (N, image size)
   uint32_t seen_N = 0; int seen_W = 0, seen_H = 0;
-  int pending_total = 0;       // 1: an asynchronous count is in flight (ev_total / h_total not consumed yet)
+  // asynchronous-count mode: counts in flight (FIFO ring of pinned slots + events; consumed by non-blocking polls)
+  static constexpr int kRing = 64;
+  int64_t* h_ring = nullptr;           // pinned [kRing][2]: duplicates, visible Gaussians
+  cudaEvent_t ev_ring[kRing] = {};
+  int64_t ring_gen[kRing] = {};        // generation of the forward that owns the slot
+  int64_t ring_cap[kRing] = {};        // tile-list capacity that forward's sort covered
+  unsigned long long ring_head = 0, ring_tail = 0;
+  int64_t overflow_gen = 0;            // first generation found to have overflowed and not reported yet (0 = none)
+  int64_t overflow_dup = 0, overflow_cap = 0;
   int64_t generation = 0;      // stamp of the forward whose state the context holds (0 = none)
   int64_t N_visible = -1;
   int sorted_sel = 0;          // which vals[] holds the sorted ids

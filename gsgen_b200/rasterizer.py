@@ -187,9 +187,11 @@ def render_view(mean, qvec, svec, alpha, c2w, camera_info, *, color=None, sh=Non
                 context holds ONE view between its forward and its backward: every view that is in flight at the same
                 time (a batch rendered before one loss.backward()) needs its own slot; the backward raises if its slot
                 was overwritten.
-    async_count: no host wait in the forward (GSB200_OPT_ASYNC_COUNT, include/gsb200.h): the tile sort covers a capacity
-                learnt from the slot's earlier views; aux["N_with_dub"] is None; the backward (or `view_stats`) raises
-                `_lib.TileListOverflow` if the view did not fit -- render it again.
+    async_count: no host wait in forward or backward (GSB200_OPT_ASYNC_COUNT, include/gsb200.h): the tile sort covers a
+                capacity learnt from the slot's earlier views, aux["N_with_dub"] is None, and the exact count is polled
+                later.  A view that did not fit raises `_lib.TileListOverflow` from the first forward / backward on the
+                slot that sees its count -- usually its own backward -- or from `view_stats(device, slot)`, which
+                waits for it: render that view again.
 
     color given -> RGB path (render_with_T + 3x render_scalar semantics, per-pixel bg[H,W,3]);
     sh given    -> SH path  (render_sh / render_sh_bg semantics, constant bg_rgb[3]); `sh_c2w` is the tensor the

@@ -48,16 +48,24 @@ int gsb200_ctx_destroy(gsb200_ctx* ctx);
  *   GSB200_OPT_BWD_SH_VARIANT  0 (default): SH backward flushes a warp's partial sums straight to global memory with
  *                              vector reductions (csrc/composite_bwd_sh.cu); 1: round-1 kernel (per-batch shared
  *                              accumulator).  Both implement vol_render_sh.h:353-455; kept switchable for A/B timing.
- *   GSB200_OPT_ASYNC_COUNT     0 (default): gsb200_render_forward waits for the view's duplicate count (8 bytes; the
- *                              one host wait of a view -- the reference blocks twice, gs/culling.py:33-35 and
- *                              aabb_culling.h:227).  1: no host wait: the tile sort covers a capacity learnt from the
- *                              earlier views of this context (largest N_with_dub seen + 1/8; the first view of a
- *                              context, or after N / the image size changed, is synchronous), *h_num_dup is -1, and the
- *                              exact count is consumed by gsb200_render_backward / gsb200_view_stats, which return
- *                              GSB200_ERR_OVERFLOW if the view did not fit (render it again: the capacity was raised).
+ *   GSB200_OPT_ASYNC_COUNT     0 (default): gsb200_render_forward waits for the view's duplicate count (16 bytes;
+ *                              the one host wait of a view -- the reference blocks twice, gs/culling.py:33-35 and
+ *                              aabb_culling.h:227).  1: NO host wait anywhere in forward or backward, so the host can
+ *                              run many views ahead of the GPU (a descheduled host thread no longer stalls the
+ *                              device): the tile sort covers a capacity learnt from the earlier views of this context
+ *                              (largest N_with_dub seen + 1/8; the first view of a context, or after N / the image
+ *                              size changed, is synchronous), *h_num_dup is -1, and the exact count travels through a
+ *                              ring of pinned slots that later calls on the context poll without blocking.  A view
+ *                              whose lists exceeded the capacity is reported as GSB200_ERR_OVERFLOW by the first
+ *                              render_forward / render_backward on the context that sees its count (usually the
+ *                              view's own backward) or by gsb200_view_stats, which waits for all counts in flight:
+ *                              that view's images / gradients are truncated -- render it again (capacity raised).
  */
 #define GSB200_OPT_BWD_SH_VARIANT 1
 #define GSB200_OPT_ASYNC_COUNT 2
+#define GSB200_OPT_FWD_SH_VARIANT 3 /* SH degree >= 2 forward: 0 one pixel per thread (256 threads per tile), 1 two  */
+                                    /* pixels per thread (128 threads per tile; one coefficient read feeds two dot    */
+                                    /* products).  Same per-pixel arithmetic; switchable for A/B timing.               */
 int gsb200_ctx_set_option(gsb200_ctx* ctx, int option, int64_t value);
 
 /* ================================================================================================
