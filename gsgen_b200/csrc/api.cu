@@ -326,7 +326,7 @@ int gsb200_tile_based_vol_rendering_sh(
   fill_common(a, ctx, start, end, ids, topleft, th, tw, psx, psy, H, W, thresh);
   a.sh = sh; a.c9_ptr = c2w; a.bg_rgb = bg_rgb;
   a.out = out;
-  if (C >= 3 && ctx->fwd_sh_variant == 1) return launch_composite_fwd_sh2((int)C, a, st);
+  if (C >= 3 && ctx->fwd_sh_variant == 1) return launch_composite_fwd_shh((int)C, a, st);
   return launch_composite_fwd(PAY_SH, (int)C, false, a, st);
 }
 
@@ -510,7 +510,7 @@ int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb
   a.depth = out->depth; a.opacity = out->opacity; a.z2 = out->z2;
   a.stats = ctx->profiling ? ctx->d_stats.as<unsigned long long>() : nullptr;
   if (is_sh && in->C >= 3 && ctx->fwd_sh_variant == 1) {
-    if ((rc = launch_composite_fwd_sh2(in->C, a, st))) return rc;
+    if ((rc = launch_composite_fwd_shh(in->C, a, st))) return rc;
   } else if ((rc = launch_composite_fwd(is_sh ? PAY_SH : PAY_RGB, is_sh ? in->C : 1, extras, a, st))) {
     return rc;
   }

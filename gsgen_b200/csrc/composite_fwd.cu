@@ -21,9 +21,6 @@ namespace gsb {
 #ifndef GSB_FWD_MINBLOCKS
 #define GSB_FWD_MINBLOCKS 0  // 0: no minBlocksPerSM hint (48 registers at SH deg 3 -> 5 CTAs/SM).  Note: a hint of 1 is
 #endif                       // NOT neutral -- ptxas then spends 81 registers (3 CTAs/SM); 6 caps it at 40.
-#ifndef GSB_FWD_NW
-#define GSB_FWD_NW 8         // warps per CTA: 8 = one CTA per 16x16 tile, 4 = two CTAs per tile (SH degree >= 2 only)
-#endif
 #if GSB_FWD_MINBLOCKS > 0
 #define GSB_FWD_BOUNDS __launch_bounds__(kCtaThreads, GSB_FWD_MINBLOCKS)
 #else
@@ -43,7 +40,7 @@ k_composite_fwd(const CompositeArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y;
   const int tile = tile_y * a.tiles_w + tile_x;
-  const PixelGeom pg = pixel_geom(a, tile_x, tile_y, warp + (int)blockIdx.z * (int)(blockDim.x >> 5), lane);
+  const PixelGeom pg = pixel_geom(a, tile_x, tile_y, warp, lane);
   const int pix = pg.gy * a.W + pg.gx;
 
   const int s0 = a.start[tile];
@@ -238,10 +235,8 @@ static int launch_one(const CompositeArgs& a, cudaStream_t st) {
   const size_t smem = 2 * (size_t)L::kBytes;
   auto kern = k_composite_fwd<PAY, C, EXTRAS, B>;
   GSB_CUDA(ensure_max_dyn_smem(reinterpret_cast<const void*>(kern), (int)smem, a.device));
-  // half-tile CTAs (GSB_FWD_NW == 4) for the staged-SH instantiations whose batch fits 128 staging threads
-  const int nw = (PAY == PAY_SH && C >= 3 && B <= 128) ? GSB_FWD_NW : 8;
-  dim3 grid(a.tiles_w, a.tiles_h, 8 / nw);
-  kern<<<grid, nw * 32, smem, st>>>(a);
+  dim3 grid(a.tiles_w, a.tiles_h, 1);
+  kern<<<grid, kCtaThreads, smem, st>>>(a);
   GSB_LAUNCH_CHECK();
   return GSB200_OK;
 }
