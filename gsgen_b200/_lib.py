@@ -21,7 +21,7 @@ c_f32 = ctypes.c_float
 c_i64 = ctypes.c_int64
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_MISMATCH, ERR_OVERFLOW = 0, 1, 2, 3, 4, 5
-OPT_BWD_SH_VARIANT, OPT_ASYNC_COUNT, OPT_FWD_SH_VARIANT = 1, 2, 3  # GSB200_OPT_* (include/gsb200.h)
+OPT_BWD_SH_VARIANT, OPT_ASYNC_COUNT = 1, 2  # GSB200_OPT_* (include/gsb200.h)
 
 
 class Gsb200Camera(ctypes.Structure):

@@ -175,7 +175,6 @@ int gsb200_ctx_create(int device, gsb200_ctx** out) {
   // tuning / A-B defaults from the environment (the options themselves: gsb200_ctx_set_option)
   if (const char* e = getenv("GSB200_BWD_SH_VARIANT")) c->bwd_sh_variant = atoi(e);
   if (const char* e = getenv("GSB200_ASYNC_COUNT")) c->async_count = atoi(e) ? 1 : 0;
-  if (const char* e = getenv("GSB200_FWD_SH_VARIANT")) c->fwd_sh_variant = atoi(e) ? 1 : 0;
   *out = c;
   return GSB200_OK;
 }
@@ -326,7 +325,6 @@ int gsb200_tile_based_vol_rendering_sh(
   fill_common(a, ctx, start, end, ids, topleft, th, tw, psx, psy, H, W, thresh);
   a.sh = sh; a.c9_ptr = c2w; a.bg_rgb = bg_rgb;
   a.out = out;
-  if (C >= 3 && ctx->fwd_sh_variant == 1) return launch_composite_fwd_shh((int)C, a, st);
   return launch_composite_fwd(PAY_SH, (int)C, false, a, st);
 }
 
@@ -509,11 +507,7 @@ int gsb200_render_forward(gsb200_ctx* ctx, const gsb200_camera* camin, const gsb
   a.out = out->rgb; a.T = out->T;
   a.depth = out->depth; a.opacity = out->opacity; a.z2 = out->z2;
   a.stats = ctx->profiling ? ctx->d_stats.as<unsigned long long>() : nullptr;
-  if (is_sh && in->C >= 3 && ctx->fwd_sh_variant == 1) {
-    if ((rc = launch_composite_fwd_shh(in->C, a, st))) return rc;
-  } else if ((rc = launch_composite_fwd(is_sh ? PAY_SH : PAY_RGB, is_sh ? in->C : 1, extras, a, st))) {
-    return rc;
-  }
+  if ((rc = launch_composite_fwd(is_sh ? PAY_SH : PAY_RGB, is_sh ? in->C : 1, extras, a, st))) return rc;
   GSB_EV(ev, 4, st);
   return GSB200_OK;
 }
@@ -700,10 +694,6 @@ int gsb200_ctx_set_option(gsb200_ctx* ctx, int option, int64_t value) {
       return GSB200_OK;
     case GSB200_OPT_ASYNC_COUNT:
       ctx->async_count = value ? 1 : 0;
-      return GSB200_OK;
-    case GSB200_OPT_FWD_SH_VARIANT:
-      GSB_CHECK(value == 0 || value == 1, GSB200_ERR_INVALID, "fwd_sh_variant must be 0 or 1");
-      ctx->fwd_sh_variant = (int)value;
       return GSB200_OK;
     default:
       break;

@@ -84,7 +84,6 @@ struct gsb200_ctx {
   // options (gsb200_ctx_set_option)
   int bwd_sh_variant = 0;      // 0: direct vector-reduction flush (composite_bwd_sh.cu); 1: round-1 shared accumulator
   int async_count = 0;         // 1: render_forward does not wait for N_with_dub (capacity from earlier views)
-  int fwd_sh_variant = 0;      // 0: warp = one 8x4 block (composite_fwd.cu); 1: two 4x4 half-warp blocks (composite_fwd_h.cu)
   // saved view state
   uint32_t N = 0;
   int64_t D = 0;               // exact duplicate count of the last view, -1 while unresolved (async-count mode)

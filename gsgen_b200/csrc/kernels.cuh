@@ -99,8 +99,6 @@ int launch_max_list(uint32_t T, const int32_t* start, const int32_t* end, int32_
 // composite_fwd.cu / composite_bwd.cu
 int launch_composite_fwd(int pay_kind, int C, bool extras, const CompositeArgs& a, cudaStream_t st);
 int launch_composite_bwd(int pay_kind, int C, bool extras, bool fused, const CompositeArgs& a, cudaStream_t st);
-// composite_fwd_h.cu (round 2): SH degree >= 2 forward, half-warp (4x4) pixel blocks with their own hit lists
-int launch_composite_fwd_shh(int C, const CompositeArgs& a, cudaStream_t st);
 // composite_bwd_sh.cu (round 2): SH degree >= 1 with the direct vector-reduction flush
 int launch_composite_bwd_sh(int C, bool fused, const CompositeArgs& a, cudaStream_t st);
 

@@ -63,9 +63,6 @@ int gsb200_ctx_destroy(gsb200_ctx* ctx);
  */
 #define GSB200_OPT_BWD_SH_VARIANT 1
 #define GSB200_OPT_ASYNC_COUNT 2
-#define GSB200_OPT_FWD_SH_VARIANT 3 /* SH degree >= 2 forward: 0 a warp composites one 8x4 pixel block; 1 its two       */
-                                    /* half-warps composite a 4x4 block each, walking their own hit lists in lock-step  */
-                                    /* (csrc/composite_fwd_h.cu).  Same per-pixel arithmetic.                           */
 int gsb200_ctx_set_option(gsb200_ctx* ctx, int option, int64_t value);
 
 /* ================================================================================================

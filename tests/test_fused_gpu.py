@@ -8,8 +8,14 @@ import torch
 from gsgen_b200.scenes import make_scene
 from tests.util import assert_grad_close, assert_image_close, ocam_of
 
+import os
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+# north_star tolerances: images 1e-4 abs, gradients 1e-3 rel.  (Round 1 ran these end-to-end comparisons at 2e-4 / 3e-3;
+# the environment overrides exist to re-measure how much slack a change needs.)
+IMG_ATOL = float(os.environ.get("GSB_TEST_IMG_ATOL", "1e-4"))
+GRAD_RTOL = float(os.environ.get("GSB_TEST_GRAD_RTOL", "1e-3"))
 
 
 def _leaves(sc, dev):
@@ -69,15 +75,18 @@ def test_fused_rgb_view(oracle_mod, cfg):
     mk = aux["mask"]
     assert torch.allclose(a["mean2d"].detach().cpu()[mk], aux["mean2d"].detach(), rtol=2e-5, atol=1e-6)
     assert torch.allclose(a["depth"].cpu()[mk], aux["depth"].detach(), rtol=2e-6, atol=1e-6)
-    assert_image_close(out["rgb"], ref["rgb"], margin, what="rgb", atol=2e-4)
-    assert_image_close(out["opacity"].squeeze(-1), ref["opacity"].squeeze(-1), margin, what="opacity", atol=2e-4)
+    assert_image_close(out["rgb"], ref["rgb"], margin, what="rgb", atol=IMG_ATOL)
+    assert_image_close(out["opacity"].squeeze(-1), ref["opacity"].squeeze(-1), margin, what="opacity", atol=IMG_ATOL)
     zs = max(1.0, float(ref["depth"].abs().max()))
-    assert_image_close(out["depth"].squeeze(-1) / zs, ref["depth"].squeeze(-1) / zs, margin, what="depth", atol=2e-4)
+    assert_image_close(out["depth"].squeeze(-1) / zs, ref["depth"].squeeze(-1) / zs, margin, what="depth", atol=IMG_ATOL)
     assert_image_close(out["z_var"].squeeze(-1) / zs ** 2, ref["z_var"].squeeze(-1) / zs ** 2, margin, what="z_var",
                        atol=5e-4)
     # opacity + T == 1 (size-independent identity of the blend)
     assert float((out["opacity"] + out["T"] - 1).abs().max()) < 2e-5
-    tol = 3e-3  # end-to-end: projection differences + flips feed the 1e-3 per-op tolerance
+    # the "dense" scene is built to stress the 1/255 skip test (svec x4: 30+ pixels sit within 2e-3 of the threshold and
+    # take the other branch than the fp64 CPU oracle); each such pixel moves the gradient by a whole blend step.
+    # Measured round 2: g_svec 1.5e-3 rel l2 there, < 5e-4 everywhere else -> 3e-3 for this one case, 1e-3 otherwise.
+    tol = GRAD_RTOL if cfg != "dense" else max(GRAD_RTOL, 3e-3)
     assert_grad_close(mg.grad, mo.grad, tol, "g_mean")
     assert_grad_close(qg.grad, qo.grad, tol, "g_qvec")
     assert_grad_close(sg.grad, so.grad, tol, "g_svec")
@@ -121,8 +130,8 @@ def test_fused_sh_view(oracle_mod, C, with_bg):
     (out["rgb"] * w_rgb.to(DEV)).sum().backward()
     assert torch.equal(out["aux"]["mask"].cpu(), aux["mask"])
     assert out["aux"]["N_with_dub"] == aux["D"]
-    assert_image_close(out["rgb"], ref["rgb"], margin, what=f"sh rgb C={C}", atol=2e-4)
-    tol = 3e-3
+    assert_image_close(out["rgb"], ref["rgb"], margin, what=f"sh rgb C={C}", atol=IMG_ATOL)
+    tol = GRAD_RTOL
     assert_grad_close(mg.grad, mo.grad, tol, "g_mean")
     assert_grad_close(qg.grad, qo.grad, tol, "g_qvec")
     assert_grad_close(sg.grad, so.grad, tol, "g_svec")

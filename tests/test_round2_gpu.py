@@ -256,3 +256,35 @@ def test_two_gpu_replicas_stay_bit_identical():
     mp.spawn(_replica_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     assert ret["same"], "arenas (parameters, gradients, Adam moments) differ between the two ranks"
     assert ret["sizes"][2][0] != ret["sizes"][2][1], "densify / prune did not run: the test exercises nothing"
+
+
+def test_viewer_loop_renders_uint8_frames_in_eval_mode():
+    """the viewer side (utils/viewer/viser_viewer.py:129-171): eval-mode render_one under no_grad -> uint8 frame, equal to
+    the reference's host-side expression applied to the same image; nothing touches the gradient arena or the statistics"""
+    import numpy as np
+
+    from gsgen_b200.splatting import GaussianSplattingRenderer
+    from gsgen_b200.viewer import ViewerLoop
+
+    sc = _small_scene(N=6000, reso=128)
+    r = GaussianSplattingRenderer({}, _raw_init(sc), device=DEV).eval()
+    loop = ViewerLoop(r, resolution=200)
+    q = np.array([0.0, 1.0, 0.0, 0.0])  # (w,x,y,z): some rotation; the camera looks at the scene from a distance
+    from gsgen_b200.camera import orbit_c2w
+
+    c2w = orbit_c2w(2.5, 15.0, 30.0).numpy()
+    # a rotation matrix -> quaternion for the viewer interface (w,x,y,z)
+    R = c2w[:3, :3]
+    w_ = np.sqrt(max(0.0, 1 + R[0, 0] + R[1, 1] + R[2, 2])) / 2
+    q = np.array([w_, (R[2, 1] - R[1, 2]) / (4 * w_), (R[0, 2] - R[2, 0]) / (4 * w_), (R[1, 0] - R[0, 1]) / (4 * w_)])
+    frame = loop.render_frame(fov=0.8, aspect=1.25, wxyz=q, position=c2w[:3, 3])
+    assert frame.dtype == np.uint8 and frame.shape == (160, 200, 3) and frame.max() > 0
+    with torch.no_grad():
+        from gsgen_b200.camera import CameraInfo
+        from gsgen_b200.viewer import get_c2w
+
+        cam = CameraInfo.from_fov_camera(0.8, 1.25, 200, 0.01, 100.0)
+        img = r.render_one(torch.from_numpy(get_c2w(q, c2w[:3, 3])), cam)["rgb"]
+    want = (img.detach().cpu().clamp(min=0.0, max=1.0).numpy() * 255.0).astype(np.uint8)
+    assert np.array_equal(frame, want)
+    assert float(r.store.flat_grad.abs().max()) == 0 and not r._pending and loop.fps > 0
