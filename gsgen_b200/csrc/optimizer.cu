@@ -10,12 +10,15 @@
 
 namespace gsb {
 
-__device__ __forceinline__ float field_step_size(const AdamFields& F, unsigned long long i) {
-  float s = F.step_size[0];
+__device__ __forceinline__ int field_of(const AdamFields& F, unsigned long long i) {
+  int k = 0;
 #pragma unroll
   for (int f = 1; f < 8; ++f)
-    if (f < F.n && i >= F.begin[f]) s = F.step_size[f];
-  return s;
+    if (f < F.n && i >= F.begin[f]) k = f;
+  return k;
+}
+__device__ __forceinline__ float field_step_size(const AdamFields& F, unsigned long long i) {
+  return F.step_size[field_of(F, i)];
 }
 
 __global__ void __launch_bounds__(256)
@@ -29,9 +32,12 @@ k_adam_flat(float* __restrict__ param, const float* __restrict__ grad, float* __
     const float4 g = reinterpret_cast<const float4*>(grad)[q];
     float4 m = reinterpret_cast<float4*>(exp_avg)[q];
     float4 v = reinterpret_cast<float4*>(exp_avg_sq)[q];
-    const float s0 = field_step_size(F, i), s3 = field_step_size(F, i + 3);
+    const int f0 = field_of(F, i), f3 = field_of(F, i + 3);
+    const float s0 = F.step_size[f0], s3 = F.step_size[f3];
     float s1 = s0, s2 = s0;
-    if (s0 != s3) { s1 = field_step_size(F, i + 1); s2 = field_step_size(F, i + 2); }  // straddles a field boundary
+    // straddles a field boundary: compare FIELD INDICES (equal step sizes of the outer fields say nothing about a
+    // one- or two-element field in between; round-1 advice)
+    if (f0 != f3) { s1 = field_step_size(F, i + 1); s2 = field_step_size(F, i + 2); }
     adam_update(p.x, g.x, m.x, v.x, s0, K);
     adam_update(p.y, g.y, m.y, v.y, s1, K);
     adam_update(p.z, g.z, m.z, v.z, s2, K);
