@@ -86,6 +86,8 @@ def parse():
                          "tile sort (GSB200_OPT_ASYNC_COUNT)")
     ap.add_argument("--no-c4-strong", action="store_true", help="skip the C4 strong-scaling sub-record")
     ap.add_argument("--no-ref-ext", action="store_true", help="skip the reference-extension comparison (N=1 only)")
+    ap.add_argument("--dense-allreduce", action="store_true",
+                    help="N>1: all-reduce the whole flat gradient buffer instead of the rows some view touched")
     ap.add_argument("--plain-grad-buffer", action="store_true",
                     help="N>1: do not allocate the all-reduce operand with ncclMemAlloc / register it")
     return ap.parse_args()
@@ -372,7 +374,8 @@ class Workload:
         self.cams, self.c2ws_cpu = make_views(wl, self.scene, self.n_views)
         sc = self.scene
         self.vpr = ViewParallelRenderer(dict(mean=sc.mean, qvec=sc.qvec, svec=sc.svec, alpha=sc.alpha, sh=sc.sh),
-                                        self.C, dev, register_nccl=(world > 1 and not args.plain_grad_buffer))
+                                        self.C, dev, register_nccl=(world > 1 and not args.plain_grad_buffer),
+                                        sparse_allreduce=(world > 1 and not args.dense_allreduce))
         self.mine = shard_views(self.n_views, rank, world)
         self.gouts = {}
         for v in self.mine:
@@ -447,6 +450,14 @@ def warm_up(args, step, world, dev):
     for _ in range(n_extra):
         step()
     torch.cuda.synchronize()
+
+
+def allreduce_bytes(vpr):
+    """bytes the step's gradient collective(s) carried (sparse: the union's rows + the 1-byte-per-Gaussian mask)"""
+    la = vpr.last_allreduce
+    if la["mode"] == "sparse":
+        return la["rows"] * vpr._row_floats * 4 + vpr.N
+    return vpr.grad_bytes() + (vpr.N if getattr(vpr, "sparse", False) else 0)
 
 
 def time_allreduce(w, barrier, world, dev, reps=10):
@@ -782,7 +793,8 @@ def run_ours(args):
             c4 = {"workload": workload_name("c4", w4.scene, cam4), "scaling": "strong", "views_per_step": 8,
                   "views_per_gpu": len(w4.mine), "ms_per_step": ms4, "ms_per_step_all_runs": [x[0] for x in r4],
                   "value": 8 * w4.scene.N * cam4.h * cam4.w / (ms4 / 1e3), "unit": UNIT,
-                  "grad_allreduce_bytes": w4.vpr.grad_bytes() if world > 1 else 0,
+                  "grad_allreduce_bytes": allreduce_bytes(w4.vpr) if world > 1 else 0,
+                  "allreduce": dict(w4.vpr.last_allreduce, of=w4.scene.N) if world > 1 else None,
                   "allreduce_ms": time_allreduce(w4, barrier, world, dev),
                   "allreduce_buffer": w4.vpr.grad_buffer_kind, "tile_list_overflows": w4.overflows,
                   "note": "speed-up over N=1 = ms_per_step(N=1) / ms_per_step(N); north_star target >= 6x at N=8"}
@@ -829,7 +841,9 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(wl, scene, cams[0]), "views_per_step": n_views,
                    "views_per_gpu": len(mine), "parallelism": f"view-dp{world}",
-                   "grad_allreduce_bytes": vpr.grad_bytes() if world > 1 else 0,
+                   "grad_allreduce_bytes": allreduce_bytes(vpr) if world > 1 else 0,
+                   "grad_allreduce_dense_bytes": vpr.grad_bytes() if world > 1 else 0,
+                   "allreduce": dict(vpr.last_allreduce, of=scene.N) if world > 1 else None,
                    "allreduce_buffer": vpr.grad_buffer_kind if world > 1 else None,
                    "count_mode": args.count_mode,
                    "l2": "no explicit flush: inputs larger than L2 -- per step %.0f MB of Gaussian parameters + as many "

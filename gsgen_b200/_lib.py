@@ -79,6 +79,7 @@ class Gsb200ViewGrads(ctypes.Structure):
         ("g_color", c_void), ("g_sh", c_void), ("g_mean2d", c_void), ("g_bg", c_void),
         ("accumulate", c_i32),
         ("generation", c_i64),
+        ("touched", c_void),
     ]
 
 
@@ -96,7 +97,7 @@ EXPORTS = [
     "gsb200_project_gaussians_forward", "gsb200_project_gaussians_backward", "gsb200_tile_culling_aabb_count",
     "gsb200_render_forward", "gsb200_render_backward", "gsb200_view_stats",
     "gsb200_ctx_set_profiling", "gsb200_ctx_get_profile", "gsb200_adam_step", "gsb200_ctx_set_option",
-    "gsb200_store_compact", "gsb200_store_append",
+    "gsb200_store_compact", "gsb200_store_append", "gsb200_rows_pack", "gsb200_rows_unpack",
 ]
 
 

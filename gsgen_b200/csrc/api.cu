@@ -581,7 +581,7 @@ int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* camin, const gs
   rc = launch_project_bwd_fused(N, in->mean, in->qvec, in->svec, in->alpha, is_sh ? nullptr : in->color, in->act,
                                 g->mask, cam, ctx->ggeom.as<float4>(), is_sh ? nullptr : ctx->gpay.as<float4>(),
                                 g->g_mean, g->g_qvec, g->g_svec, g->g_alpha, is_sh ? nullptr : g->g_color,
-                                g->g_mean2d, g->accumulate, st);
+                                g->g_mean2d, g->accumulate, g->touched, st);
   if (rc) return rc;
   GSB_EV(ev, 2, st);
   return GSB200_OK;

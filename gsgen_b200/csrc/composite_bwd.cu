@@ -398,7 +398,7 @@ k_composite_bwd(const CompositeArgs a) {
         for (int k = 0; k < 6; ++k) { g[k] = row[BT::kGeoOff + k]; row[BT::kGeoOff + k] = 0.f; }
         if constexpr (FUSED) {
           red_add_v4(a.ggeom + (size_t)id * 8, g[0], g[1], g[2], g[3]);
-          red_add_v4(a.ggeom + (size_t)id * 8 + 4, g[4], g[5], 0.f, 0.f);
+          red_add_v4(a.ggeom + (size_t)id * 8 + 4, g[4], g[5], 0.f, 1.0f);  // .w: touch counter
         } else {
           red_add_v2(a.grad_mean + (size_t)id * 2, g[0], g[1]);
           red_add_v4(a.grad_cov + (size_t)id * 4, g[2], g[3], g[3], g[4]);
@@ -416,7 +416,7 @@ k_composite_bwd(const CompositeArgs a) {
           float gd = 0.f;
           if constexpr (PAY == PAY_RGB && EXTRAS) gd = g[9];
           red_add_v4(a.ggeom + (size_t)id * 8, g[0], g[1], g[2], g[3]);
-          red_add_v4(a.ggeom + (size_t)id * 8 + 4, g[4], g[5], gd, 0.f);
+          red_add_v4(a.ggeom + (size_t)id * 8 + 4, g[4], g[5], gd, 1.0f);  // .w: touch counter
         } else {
           red_add_v2(a.grad_mean + (size_t)id * 2, g[0], g[1]);
           red_add_v4(a.grad_cov + (size_t)id * 4, g[2], g[3], g[3], g[4]);

@@ -137,9 +137,9 @@ __device__ __noinline__ void flush_direct(const FlushDst a, const float* my_t, c
   if (lane < nslot * 6 && (lane % 6) == 0) {
     const int hh = lane / 6;
     const int id = ids_stage[(slots >> (8 * hh)) & 255u];
-    if constexpr (FUSED) {  // {gmx, gmy, gxx, gxy | gyy, galpha, gdepth, -}
+    if constexpr (FUSED) {  // {gmx, gmy, gxx, gxy | gyy, galpha, gdepth, #flushes}
       red_add_v4(a.g0 + (size_t)id * 8, s, s1, s2, s3);
-      red_add_v2(a.g0 + (size_t)id * 8 + 4, s4, s5);
+      red_add_v4(a.g0 + (size_t)id * 8 + 4, s4, s5, 0.f, 1.0f);  // .w counts the flushes: != 0 <=> the Gaussian was touched
     } else {
       red_add_v2(a.g0 + (size_t)id * 2, s, s1);
       red_add_v4(a.g1 + (size_t)id * 4, s2, s3, s3, s4);

@@ -75,7 +75,7 @@ int launch_preprocess(uint32_t N, const float* mean, const float* qvec, const fl
 int launch_project_bwd_fused(uint32_t N, const float* mean, const float* qvec, const float* svec,
                              const float* alpha, const float* color, int act, const uint8_t* mask, const Camera& cam, const float4* ggeom, const float4* gpay,
                              float* g_mean, float* g_qvec, float* g_svec, float* g_alpha, float* g_color,
-                             float* g_mean2d, int accumulate, cudaStream_t st);
+                             float* g_mean2d, int accumulate, uint8_t* touched, cudaStream_t st);
 
 // optimizer.cu
 struct AdamFields {

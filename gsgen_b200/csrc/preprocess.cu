@@ -226,7 +226,8 @@ k_project_bwd_fused(uint32_t N, const float* __restrict__ mean, const float* __r
                     const float* __restrict__ color, int act, const uint8_t* __restrict__ mask, Camera cam,
                     const float4* __restrict__ ggeom, const float4* __restrict__ gpay, float* __restrict__ g_mean,
                     float* __restrict__ g_qvec, float* __restrict__ g_svec, float* __restrict__ g_alpha,
-                    float* __restrict__ g_color, float* __restrict__ g_mean2d, int accumulate) {
+                    float* __restrict__ g_color, float* __restrict__ g_mean2d, int accumulate,
+                    uint8_t* __restrict__ touched) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   float gx[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f};
@@ -248,6 +249,7 @@ k_project_bwd_fused(uint32_t N, const float* __restrict__ mean, const float* __r
   }
   if (vis) {
     float4 g0 = ggeom[2 * i], g1 = ggeom[2 * i + 1];
+    if (touched && g1.w != 0.f) touched[i] = 1;  // the composite backward flushed into this Gaussian (sparse all-reduce)
     float x[3] = {mean[3 * i], mean[3 * i + 1], mean[3 * i + 2]};
     float4 q4 = reinterpret_cast<const float4*>(qvec)[i];
     float q[4] = {q4.x, q4.y, q4.z, q4.w};
@@ -353,10 +355,10 @@ int launch_preprocess(uint32_t N, const float* mean, const float* qvec, const fl
 int launch_project_bwd_fused(uint32_t N, const float* mean, const float* qvec, const float* svec,
                              const float* alpha, const float* color, int act, const uint8_t* mask, const Camera& cam, const float4* ggeom, const float4* gpay,
                              float* g_mean, float* g_qvec, float* g_svec, float* g_alpha, float* g_color,
-                             float* g_mean2d, int accumulate, cudaStream_t st) {
+                             float* g_mean2d, int accumulate, uint8_t* touched, cudaStream_t st) {
   if (N == 0) return GSB200_OK;
   k_project_bwd_fused<<<grid1d(N), kThreads, 0, st>>>(N, mean, qvec, svec, alpha, color, act, mask, cam, ggeom, gpay, g_mean, g_qvec,
-                                                     g_svec, g_alpha, g_color, g_mean2d, accumulate);
+                                                     g_svec, g_alpha, g_color, g_mean2d, accumulate, touched);
   GSB_LAUNCH_CHECK();
   return GSB200_OK;
 }

@@ -12,6 +12,8 @@
 // parameter rows are copied behind row N of every field and their gradient / moment rows are zeroed (the reference
 // concatenates zeros_like, :497-505).  Both kernels are pure HBM streams: 2 x 4 B per moved float.
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "gsb200_common.cuh"
 #include "kernels.cuh"
@@ -77,11 +79,131 @@ k_append_rows(const AppendArgs a) {
     dst[j] = (b == 0) ? src[j] : 0.f;
 }
 
+// ---- sparse gradient all-reduce: pack / unpack of the rows some view touched ---------------------
+// T < T_thresh hides most of a scene from any one view (measured with the oracle: a view sends gradients to 10 % of
+// C3's Gaussians, the 8 views of a step to 36 %), so the flat gradient buffer the ranks all-reduce is mostly zeros.
+// pack: rows with keep[i] != 0 of every field are gathered into a TIGHT buffer -- field f starts at
+// n_keep * (sum of the widths before f) -- so the ranks (which hold the same OR-reduced mask) all-reduce n_keep * 59
+// floats with ONE collective; unpack scatters the reduced rows back.
+struct KeepFlag {
+  const uint8_t* m;
+  __host__ __device__ __forceinline__ int32_t operator()(int i) const { return m[i] ? 1 : 0; }
+};
+
+struct PackArgs {
+  unsigned long long off[kMaxFields];  // field offsets in the flat buffer
+  unsigned long long poff[kMaxFields]; // field offsets in the packed buffer (n_keep based)
+  uint32_t width[kMaxFields];
+  uint32_t N;
+};
+
+__global__ void __launch_bounds__(256)
+k_kept_ids(uint32_t N, const uint8_t* __restrict__ keep, const int32_t* __restrict__ excl, int32_t* __restrict__ idx) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N && keep[i]) idx[excl[i]] = (int32_t)i;
+}
+
+// grid: x over the elements of the KEPT rows of a field (grid-stride), y = field.  Packed side coalesced; flat side
+// whole rows (contiguous width_f floats) at the kept row's position.
+template <bool PACK>
+__global__ void __launch_bounds__(256)
+k_pack_rows(const PackArgs a, float* __restrict__ flat, float* __restrict__ packed, const int32_t* __restrict__ idx,
+            uint32_t n_keep) {
+  const int f = blockIdx.y;
+  const uint32_t w = a.width[f];
+  float* __restrict__ fl = flat + a.off[f];
+  float* __restrict__ pk = packed + a.poff[f];
+  const unsigned long long n_el = (unsigned long long)n_keep * w;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_el; j += stride) {
+    const uint32_t r = (uint32_t)(j / w), e = (uint32_t)(j - (unsigned long long)r * w);
+    const unsigned long long src = (unsigned long long)idx[r] * w + e;
+    if (PACK) pk[j] = fl[src]; else fl[src] = pk[j];
+  }
+}
+
 }  // namespace gsb
 
 using namespace gsb;
 
 extern "C" {
+
+int gsb200_rows_pack(gsb200_ctx* ctx, const float* flat, float* packed, uint64_t packed_capacity,
+                     const uint64_t* h_field_off, const uint32_t* h_field_width, int32_t n_fields, uint32_t N,
+                     const uint8_t* keep, int32_t* idx, uint32_t* h_n_keep, gsb200_stream stream) {
+  GSB_CHECK(ctx != nullptr, GSB200_ERR_INVALID, "null context");
+  GSB_CUDA(cudaSetDevice(ctx->device));
+  GSB_CHECK(flat && packed && h_field_off && h_field_width && keep && idx && h_n_keep, GSB200_ERR_INVALID,
+            "rows_pack: null argument");
+  GSB_CHECK(n_fields >= 1 && n_fields <= kMaxFields, GSB200_ERR_INVALID, "rows_pack: n_fields=%d (1..8)", n_fields);
+  GSB_CHECK(N < 2147483647u, GSB200_ERR_INVALID, "rows_pack: N exceeds int32");
+  cudaStream_t st = (cudaStream_t)stream;
+  *h_n_keep = 0;
+  if (N == 0) return GSB200_OK;
+  int rc;
+  if ((rc = ctx->incl.reserve((size_t)N * 4))) return rc;
+  int32_t* excl = ctx->incl.as<int32_t>();
+  auto flags = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), KeepFlag{keep});
+  size_t bytes = 0;
+  GSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, flags, excl, (int)N, st));
+  if ((rc = ctx->cub_tmp.reserve(bytes))) return rc;
+  GSB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, bytes, flags, excl, (int)N, st));
+  k_kept_ids<<<(N + 255) / 256, 256, 0, st>>>(N, keep, excl, idx);
+  GSB_LAUNCH_CHECK();
+  int32_t h_last = 0;
+  uint8_t h_flag = 0;
+  GSB_CUDA(cudaMemcpyAsync(&h_last, excl + (N - 1), 4, cudaMemcpyDeviceToHost, st));
+  GSB_CUDA(cudaMemcpyAsync(&h_flag, keep + (N - 1), 1, cudaMemcpyDeviceToHost, st));
+  GSB_CUDA(cudaStreamSynchronize(st));  // the collective's element count is a host quantity: the one sync
+  const uint32_t n_keep = (uint32_t)h_last + (h_flag ? 1u : 0u);
+  *h_n_keep = n_keep;
+  PackArgs a;
+  memset(&a, 0, sizeof(a));
+  unsigned long long row = 0, widest = 1;
+  for (int f = 0; f < n_fields; ++f) {
+    a.off[f] = h_field_off[f]; a.width[f] = h_field_width[f];
+    a.poff[f] = (unsigned long long)n_keep * row;
+    row += h_field_width[f];
+    widest = a.width[f] > widest ? a.width[f] : widest;
+  }
+  a.N = N;
+  if ((unsigned long long)n_keep * row > packed_capacity) return GSB200_OK;  // does not fit: the caller reduces densely
+  if (n_keep == 0) return GSB200_OK;
+  unsigned long long blocks = ((unsigned long long)n_keep * widest + 255) / 256;
+  const unsigned long long cap_blocks = (unsigned long long)ctx->sm_count * 8;
+  if (blocks > cap_blocks) blocks = cap_blocks;
+  dim3 grid((unsigned)blocks, (unsigned)n_fields, 1);
+  k_pack_rows<true><<<grid, 256, 0, st>>>(a, const_cast<float*>(flat), packed, idx, n_keep);
+  GSB_LAUNCH_CHECK();
+  return GSB200_OK;
+}
+
+int gsb200_rows_unpack(gsb200_ctx* ctx, float* flat, const float* packed, const uint64_t* h_field_off,
+                       const uint32_t* h_field_width, int32_t n_fields, uint32_t N, const int32_t* idx,
+                       uint32_t n_keep, gsb200_stream stream) {
+  GSB_CHECK(ctx != nullptr, GSB200_ERR_INVALID, "null context");
+  GSB_CUDA(cudaSetDevice(ctx->device));
+  GSB_CHECK(flat && packed && h_field_off && h_field_width && idx, GSB200_ERR_INVALID, "rows_unpack: null argument");
+  GSB_CHECK(n_fields >= 1 && n_fields <= kMaxFields, GSB200_ERR_INVALID, "rows_unpack: n_fields=%d (1..8)", n_fields);
+  if (N == 0 || n_keep == 0) return GSB200_OK;
+  PackArgs a;
+  memset(&a, 0, sizeof(a));
+  unsigned long long row = 0, widest = 1;
+  for (int f = 0; f < n_fields; ++f) {
+    a.off[f] = h_field_off[f]; a.width[f] = h_field_width[f];
+    a.poff[f] = (unsigned long long)n_keep * row;
+    row += h_field_width[f];
+    widest = a.width[f] > widest ? a.width[f] : widest;
+  }
+  a.N = N;
+  unsigned long long blocks = ((unsigned long long)n_keep * widest + 255) / 256;
+  const unsigned long long cap_blocks = (unsigned long long)ctx->sm_count * 8;
+  if (blocks > cap_blocks) blocks = cap_blocks;
+  dim3 grid((unsigned)blocks, (unsigned)n_fields, 1);
+  k_pack_rows<false><<<grid, 256, 0, (cudaStream_t)stream>>>(a, flat, const_cast<float*>(packed), idx, n_keep);
+  GSB_LAUNCH_CHECK();
+  return GSB200_OK;
+}
 
 int gsb200_store_compact(gsb200_ctx* ctx, const float* const* h_src, float* const* h_dst, int32_t n_bufs,
                          const uint64_t* h_field_off, const uint32_t* h_field_width, int32_t n_fields, uint32_t N,

@@ -57,7 +57,7 @@ class ViewParallelRenderer:
     """
 
     def __init__(self, params: Dict[str, torch.Tensor], C: Optional[int], device, group=None,
-                 register_nccl: bool = False):
+                 register_nccl: bool = False, sparse_allreduce: bool = False, sparse_max_fraction: float = 0.6):
         self.C = C
         self.device = torch.device(device)
         self.group = group
@@ -72,6 +72,19 @@ class ViewParallelRenderer:
             self.flat_grad = self._alloc_registered(total)
         if self.flat_grad is None:
             self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        # sparse all-reduce (CUDA, world > 1): the backward marks the Gaussians it sent gradients to; the ranks
+        # MAX-reduce that byte mask and all-reduce only the union's rows (gsb200_rows_pack / _unpack).  T < T_thresh
+        # hides most of a scene from any one view: 10 % of C3's Gaussians per view, 36 % over 8 views (oracle count).
+        self.sparse = bool(sparse_allreduce) and self.world > 1 and self.device.type == "cuda"
+        self.sparse_max_fraction = float(sparse_max_fraction)
+        self.last_allreduce = {"mode": "dense", "rows": N}
+        if self.sparse:
+            self.touched = torch.zeros(N, dtype=torch.uint8, device=self.device)
+            self._excl = torch.empty(N, dtype=torch.int32, device=self.device)  # ids of the union's rows
+            row = sum(n // N for _, _, _, n in self.layout) if N else 0
+            self._row_floats = row
+            self._packed = torch.empty(int(self.sparse_max_fraction * N) * row + 64, dtype=torch.float32,
+                                       device=self.device)
         self.params: Dict[str, torch.Tensor] = {}
         self.grad_views: Dict[str, torch.Tensor] = {}
         for name, shape, off, n in self.layout:
@@ -80,6 +93,8 @@ class ViewParallelRenderer:
             p.requires_grad_(True)
             self.params[name] = p
             self.grad_views[name] = self.flat_grad[off:off + n].view(shape)
+        if self.sparse:  # render_view(grad_sink=...) hands this to the backward (gsb200_view_grads.touched)
+            self.grad_views["touched"] = self.touched
 
     def _alloc_registered(self, total: int):
         """The all-reduce operand allocated with ncclMemAlloc and registered with the communicator (NCCL user-buffer
@@ -113,12 +128,51 @@ class ViewParallelRenderer:
 
     def zero_grad(self):
         self.flat_grad.zero_()
+        if self.sparse:
+            self.touched.zero_()
         for name, p in self.params.items():
             p.grad = self.grad_views[name]  # autograd accumulates in place into the flat buffer
 
     def all_reduce(self):
-        if self.world > 1:
+        """ONE all-reduce(SUM) of the gradients per step.  Dense: the whole flat buffer.  Sparse: MAX-reduce the
+        1-byte-per-Gaussian touched mask, pack the union's rows (one host sync for the row count), all-reduce
+        rows x (11 + 3C^2) floats, unpack; falls back to the dense collective when the union exceeds
+        `sparse_max_fraction` of the Gaussians (the same decision on every rank: the mask is identical)."""
+        if self.world == 1:
+            return
+        self._n_allreduce = getattr(self, "_n_allreduce", 0) + 1
+        if not self.sparse or self._n_allreduce < getattr(self, "_dense_until", 0):
+            # (after a step whose union was too large the next 32 steps go dense without paying for the mask reduction
+            # and the row count: the touched fraction of a scene changes slowly; same decision on every rank)
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        import ctypes
+
+        from . import _lib
+
+        dist.all_reduce(self.touched, op=dist.ReduceOp.MAX, group=self.group)
+        names = [n for n, _, _, _ in self.layout]
+        offs = (ctypes.c_uint64 * len(names))(*[off for _, _, off, _ in self.layout])
+        widths = (ctypes.c_uint32 * len(names))(*[(n // self.N) for _, _, _, n in self.layout])
+        n_keep = ctypes.c_uint32(0)
+        L, c, st = _lib.lib(), _lib.ctx(self.device), _lib.stream_ptr(self.device)
+        cap = self._packed.numel()
+        _lib.check(L.gsb200_rows_pack(c, _lib.fptr(self.flat_grad), _lib.fptr(self._packed), ctypes.c_uint64(cap), offs,
+                                      widths, ctypes.c_int32(len(names)), ctypes.c_uint32(self.N),
+                                      _lib.ptr(self.touched, torch.uint8), _lib.iptr(self._excl), ctypes.byref(n_keep),
+                                      st))
+        k = int(n_keep.value)
+        if k * self._row_floats > cap:  # most Gaussians touched (e.g. C4's 8 views: 69 %): dense is cheaper
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            self.last_allreduce = {"mode": "dense (union above sparse_max_fraction)", "rows": k}
+            self._dense_until = self._n_allreduce + 32
+            return
+        if k:
+            dist.all_reduce(self._packed[: k * self._row_floats], op=dist.ReduceOp.SUM, group=self.group)
+            _lib.check(L.gsb200_rows_unpack(c, _lib.fptr(self.flat_grad), _lib.fptr(self._packed), offs, widths,
+                                            ctypes.c_int32(len(names)), ctypes.c_uint32(self.N),
+                                            _lib.iptr(self._excl), ctypes.c_uint32(k), st))
+        self.last_allreduce = {"mode": "sparse", "rows": k}
 
     def step(self, n_views: int, render_and_backward: Callable[[Dict[str, torch.Tensor], int], None]):
         """zero grads -> local views fwd+bwd (gradients accumulate) -> one all-reduce.  Returns local view ids."""

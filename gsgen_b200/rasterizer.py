@@ -158,6 +158,7 @@ class _RenderView(torch.autograd.Function):
         g.g_mean, g.g_qvec, g.g_svec, g.g_alpha = fptr(gm), fptr(gq), fptr(gs), fptr(ga)
         g.g_color, g.g_sh, g.g_mean2d, g.g_bg = fptr(gcol), fptr(gsh), fptr(gm2), fptr(gbg)
         g.generation = ctx.generation  # fails loudly if a later forward re-used this view's context slot
+        g.touched = ptr(sink["touched"], torch.uint8, "touched") if (sink is not None and "touched" in sink) else None
         c = _lib.ctx(dev, ctx.slot)
         _lib.check(_lib.lib().gsb200_render_backward(c, ctypes.byref(cam), ctypes.byref(vin), ctypes.byref(g),
                                                      _lib.stream_ptr(dev)))

@@ -255,6 +255,9 @@ typedef struct gsb200_view_grads {
   int32_t accumulate;
   int64_t generation; /* 0 = unchecked; else must equal the stamp render_forward returned: a context holds the  */
                       /* binning + splat records of ONE view, and a later forward on it overwrites them           */
+  uint8_t* touched;   /* [N] or NULL: touched[i] = 1 is written for every Gaussian the composite backward sent a   */
+                      /* gradient to (never cleared here: OR over the views of a step) -- the rows a sparse         */
+                      /* multi-GPU all-reduce has to carry (gsb200_rows_pack)                                       */
 } gsb200_view_grads;
 
 int gsb200_render_backward(gsb200_ctx* ctx, const gsb200_camera* cam, const gsb200_view_in* in,
@@ -322,6 +325,23 @@ int gsb200_store_append(gsb200_ctx* ctx, float* const* h_dst /*[n_bufs]; [0] = p
                         const float* const* h_rows /*[n_fields] device pointers to [k,width_f]*/,
                         const uint64_t* h_field_off, const uint32_t* h_field_width, int32_t n_fields, uint32_t N,
                         uint32_t k, gsb200_stream stream);
+
+/* Sparse gradient all-reduce.  A view sends gradients only to the Gaussians in front of the
+ * T < T_thresh horizon (measured: 10 % of C3's Gaussians per view, 36 % over the 8 views of a step), so the flat
+ * gradient buffer the ranks all-reduce is mostly zeros.  With gsb200_view_grads.touched the backward marks the rows it
+ * wrote; the ranks MAX-reduce that byte mask (1 B / Gaussian) and then:
+ * gsb200_rows_pack: idx[0 .. n_keep) := the ids of the rows with keep[i] != 0, in order (prefix sum + scatter; idx is
+ * the caller's [N] int32 buffer, reused by unpack), *h_n_keep = their number (ONE stream synchronisation: the
+ * collective's count is a host quantity), and -- if n_keep * row_floats <= packed_capacity -- one launch that gathers
+ * those rows of every field into `packed`, field f starting at n_keep * (widths before f): n_keep * row_floats
+ * contiguous floats for ONE collective.
+ * gsb200_rows_unpack: the reduced rows back into the flat buffer (rows not kept are left as they are: zero). */
+int gsb200_rows_pack(gsb200_ctx* ctx, const float* flat, float* packed, uint64_t packed_capacity /* floats */,
+                     const uint64_t* h_field_off, const uint32_t* h_field_width, int32_t n_fields, uint32_t N,
+                     const uint8_t* keep /*[N]*/, int32_t* idx /*[N] out*/, uint32_t* h_n_keep, gsb200_stream stream);
+int gsb200_rows_unpack(gsb200_ctx* ctx, float* flat, const float* packed, const uint64_t* h_field_off,
+                       const uint32_t* h_field_width, int32_t n_fields, uint32_t N, const int32_t* idx,
+                       uint32_t n_keep, gsb200_stream stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -288,3 +288,65 @@ def test_viewer_loop_renders_uint8_frames_in_eval_mode():
     want = (img.detach().cpu().clamp(min=0.0, max=1.0).numpy() * 255.0).astype(np.uint8)
     assert np.array_equal(frame, want)
     assert float(r.store.flat_grad.abs().max()) == 0 and not r._pending and loop.fps > 0
+
+
+def _sparse_worker(rank, world, port, ret):
+    import datetime
+
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                            timeout=datetime.timedelta(seconds=60))
+    try:
+        from gsgen_b200.camera import orbit_c2w
+        from gsgen_b200.parallel import ViewParallelRenderer
+        from gsgen_b200.rasterizer import render_view
+
+        dev = torch.device("cuda", rank)
+        sc = _small_scene(N=60001, reso=256, scale=4.0)  # N % 4 != 0 on purpose; opaque: most rows stay untouched
+        cam = sc.cams[0]
+        p = dict(mean=sc.mean, qvec=sc.qvec, svec=sc.svec, alpha=sc.alpha, sh=sc.sh)
+        out = {}
+        for sparse in (True, False):
+            vpr = ViewParallelRenderer(p, 4, dev, sparse_allreduce=sparse, sparse_max_fraction=0.9)
+            vpr.zero_grad()
+            for v in range(2):  # two views per rank
+                c2w = orbit_c2w(1.6, 15.0, 30.0 + 45.0 * (2 * rank + v))  # close: part of the ball is outside the frustum
+                g = torch.Generator().manual_seed(10 * rank + v)
+                w = torch.randn(cam.h, cam.w, 3, generator=g).to(dev)
+                o = render_view(vpr.params["mean"], vpr.params["qvec"], vpr.params["svec"], vpr.params["alpha"], c2w,
+                                cam, sh=vpr.params["sh"], C=4, slot=v, grad_sink=vpr.grad_views)
+                o["rgb"].backward(gradient=w)
+            local = vpr.flat_grad.clone()
+            vpr.all_reduce()
+            out[sparse] = (vpr.flat_grad.clone(), dict(vpr.last_allreduce), local)
+        sp, la, local = out[True]
+        dn = out[False][0]
+        ok = la["mode"] == "sparse" and 0 < la["rows"] < sc.N
+        ok = ok and torch.allclose(sp, dn, rtol=1e-5, atol=1e-6 * float(dn.abs().max()))
+        ok = ok and bool((sp[dn == 0] == 0).all())   # rows nobody touched stay exactly zero
+        ok = ok and float(dn.abs().max()) > 0
+        # every row with a local gradient is inside the union that was reduced (nothing dropped)
+        ok = ok and bool(((local != 0) <= (sp != 0) | (dn == 0)).all())
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            ret["ok"], ret["rows"], ret["N"] = bool(flag.item()), la["rows"], sc.N
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_gpu_sparse_allreduce_equals_dense():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sparse_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret["ok"], dict(ret)
+    assert ret["rows"] < 0.9 * ret["N"]
