@@ -184,7 +184,9 @@ int gsb200_ctx_destroy(gsb200_ctx* c) {
   cudaSetDevice(c->device);
   gsb::Buf* bufs[] = {&c->splat, &c->pay, &c->rect, &c->count, &c->incl, &c->ggeom, &c->gpay, &c->keys[0],
                       &c->keys[1], &c->vals[0], &c->vals[1], &c->cub_tmp, &c->start, &c->end, &c->d_total,
-                      &c->d_overflow, &c->d_small, &c->dkeys[0], &c->dkeys[1], &c->perm[0], &c->perm[1], &c->d_stats};
+                      &c->d_overflow, &c->d_small, &c->dkeys[0], &c->dkeys[1], &c->perm[0], &c->perm[1], &c->d_stats,
+                      &c->knn_keys[0], &c->knn_keys[1], &c->knn_vals[0], &c->knn_vals[1], &c->knn_pts, &c->knn_cells,
+                      &c->knn_small};
   for (auto* b : bufs) b->release();
   if (c->h_total) cudaFreeHost(c->h_total);
   if (c->h_ring) cudaFreeHost(c->h_ring);

@@ -110,6 +110,9 @@ struct gsb200_ctx {
   EvSet* fwd_sets = nullptr; int fwd_cap = 0, fwd_used = 0;
   EvSet* bwd_sets = nullptr; int bwd_cap = 0, bwd_used = 0;
   gsb::Buf d_stats;            // unsigned long long[2]: D_eff, staged
+  // K-nearest-neighbour search (knn.cu): cell keys / point order (radix sort double buffers), points in cell order,
+  // cell table, statistics + grid descriptor
+  gsb::Buf knn_keys[2], knn_vals[2], knn_pts, knn_cells, knn_small;
   int64_t sum_dup = 0;
 };
 

@@ -102,6 +102,10 @@ int launch_composite_bwd(int pay_kind, int C, bool extras, bool fused, const Com
 // composite_bwd_sh.cu (round 2): SH degree >= 1 with the direct vector-reduction flush
 int launch_composite_bwd_sh(int C, bool fused, const CompositeArgs& a, cudaStream_t st);
 
+// knn.cu: exact K nearest neighbours on a uniform grid (queries == nullptr: the points query themselves)
+int knn_device(gsb200_ctx* ctx, const float* points, uint32_t n, const float* queries, uint32_t nq, int K,
+               int64_t* idx_out, float* d2_out, cudaStream_t st);
+
 // Opt a kernel in to more than 48 KB of dynamic shared memory.  Called before every launch: the attribute is per
 // (function, device) and the call is a few hundred ns -- cheaper than a lock-protected per-device cache, and correct
 // when several host threads drive different devices through the same library (round-1 advice: the lazy

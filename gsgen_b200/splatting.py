@@ -28,7 +28,7 @@ from typing import Callable, Dict, Optional, Sequence
 
 import torch
 
-from .store import GaussianStore
+from .store import GaussianStore, quat_to_rotmat
 
 FIELDS = ("mean", "qvec", "svec", "color", "alpha")  # self.fields of the reference (:241-258)
 
@@ -78,7 +78,7 @@ class GaussianSplattingRenderer:
     (initialize(), :166-191)."""
 
     def __init__(self, cfg, initial_values: Dict[str, torch.Tensor], device="cuda", capacity: Optional[int] = None,
-                 background=None, render_fn: Optional[Callable] = None, group=None):
+                 background=None, render_fn: Optional[Callable] = None, group=None, knn_fn: Optional[Callable] = None):
         self.cfg = cfg
         self.device = torch.device(device)
         if _get(cfg, "tile_size", 16) != 16:
@@ -93,7 +93,7 @@ class GaussianSplattingRenderer:
         leaves["svec"] = svec if raw else torch.log(svec)              # inv_activations["exp"]
         leaves["color"] = color if raw else torch.logit(color)         # inv_activations["sigmoid"]
         leaves["alpha"] = (alpha if raw else torch.logit(alpha)).reshape(-1)
-        self.store = GaussianStore(leaves, None, self.device, capacity=capacity, group=group)
+        self.store = GaussianStore(leaves, None, self.device, capacity=capacity, group=group, knn_fn=knn_fn)
         self.background = background  # None (black), a [3] tensor, or callable(rays_d[H,W,3]) -> [H,W,3]
         self.training = True
         self.step = 0
@@ -117,6 +117,7 @@ class GaussianSplattingRenderer:
     svec = property(lambda self: torch.exp(self.store.params["svec"]))
     color = property(lambda self: torch.sigmoid(self.store.params["color"]))
     alpha = property(lambda self: torch.sigmoid(self.store.params["alpha"]))
+    rotmat = property(lambda self: quat_to_rotmat(self.store.params["qvec"]))  # :150-152 (kornia quat -> R)
 
     def train(self, mode: bool = True):
         self.training = mode
@@ -263,9 +264,53 @@ class GaussianSplattingRenderer:
         _scalar(writer, "auxiliary/scale_penalty_weight", w, step)
         return w * volume
 
+    def NN_penalty_loss(self, step, writer=None):
+        """:1032-1046: mean distance to the nearest other Gaussian (the neighbour is found under no_grad and enters as
+        a constant, utils/ops.py:103-114); the search is gsb200_knn (csrc/knn.cu)."""
+        from .knn import nearest_neighbor
+
+        c = self._penalty_cfg("NN")
+        w = scheduled_value(_get(c, "value", 0.0), step) if c is not None else 0.0
+        if not w > 0.0:
+            return torch.zeros_like(self.alpha[0], requires_grad=False)
+        nn_pos, _ = nearest_neighbor(self.mean, knn=self.store._knn())
+        pen = torch.mean((self.mean - nn_pos).norm(dim=-1))
+        _scalar(writer, "auxiliary/NN_penalty", pen, step)
+        _scalar(writer, "auxiliary/NN_penalty_weight", w, step)
+        return w * pen
+
+    def compat_penalty_loss(self, step, writer=None):
+        """:1048-1094: the gap between every Gaussian's "surface" and its nearest neighbour's along the line of centres
+        (utils/ops.py:137-158), where there is one -- "l1" mean gap or "l2" mean squared gap over ALL Gaussians."""
+        from .knn import distance_to_gaussian_surface, nearest_neighbor
+
+        c = self._penalty_cfg("compat")
+        w = scheduled_value(_get(c, "value", 0.0), step) if c is not None else 0.0
+        if not w > 0.0:
+            return torch.zeros_like(self.alpha[0], requires_grad=False)
+        _, idx = nearest_neighbor(self.mean, knn=self.store._knn())
+        svec, rotmat, mean = self.svec, self.rotmat, self.mean
+        nn_svec, nn_rotmat, nn_pos = svec[idx], rotmat[idx], mean[idx]
+        nn_surface = distance_to_gaussian_surface(nn_pos, nn_svec, nn_rotmat, mean)
+        surface = distance_to_gaussian_surface(mean, svec, rotmat, nn_pos)
+        dist_to_nn = torch.norm(nn_pos - mean, dim=-1)
+        mask = (surface + nn_surface) < dist_to_nn
+        kind = _get(c, "type")
+        if kind == "l1":
+            pen = torch.mean((dist_to_nn - surface - nn_surface) * mask)
+        elif kind == "l2":
+            pen = torch.mean((dist_to_nn - surface - nn_surface) ** 2 * mask)
+        else:
+            raise ValueError(f"Unknown compat penalty type: {kind}")
+        _scalar(writer, "auxiliary/compat_penalty", pen, step)
+        _scalar(writer, "auxiliary/effective_rate", torch.sum(mask).item() / self.N, step)
+        _scalar(writer, "auxiliary/compat_penalty_weight", w, step)
+        return w * pen
+
     def auxiliary_loss(self, step, writer=None):
-        """:1115-1122: the sum of `<key>_penalty_loss` over cfg.penalty.  The K-nearest-neighbour penalties (NN, compat)
-        and the PBR ones (normal, specular) belong to subsystems outside the hot path and raise here."""
+        """:1115-1122: the sum of `<key>_penalty_loss` over cfg.penalty.  Not built: `move` (the reference reads
+        `self.prev_mean`, which nothing ever sets, :1015-1030) and the PBR ones (normal, specular: fields outside the
+        hot path); they raise here."""
         loss = 0.0
         pen = _get(self.cfg, "penalty", None) or {}
         for key in (pen.keys() if hasattr(pen, "keys") else vars(pen)):

@@ -59,8 +59,11 @@ class GaussianStore:
     """
 
     def __init__(self, params: Dict[str, torch.Tensor], C: Optional[int], device=None, capacity: Optional[int] = None,
-                 growth: float = 1.5, group=None):
+                 growth: float = 1.5, group=None, knn_fn=None):
         self.C, self.group, self.growth = C, group, float(growth)
+        # neighbour search of the compactness rules: gsgen_b200.knn.knn_points (CUDA kernel) unless a callable with
+        # the same signature is plugged in (CPU tests: the oracle's brute-force search -- the product has no CPU path)
+        self.knn_fn = knn_fn
         self.device = torch.device(device) if device is not None else params["mean"].device
         self.N = int(params["mean"].shape[0])
         self.cap = self._round_cap(max(int(capacity or 0), self.N, 1))
@@ -393,6 +396,58 @@ class GaussianStore:
         self.reset_densify_info()
         return n_clone, n_split
 
+    # ---- compactness-based densification (gs/gaussian_splatting.py:634-743) ----------------------------------
+    def _knn(self):
+        if self.knn_fn is not None:
+            return self.knn_fn
+        from .knn import knn_points
+
+        return knn_points
+
+    def densify_by_compatness_with_idx(self, idx: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """:634-680.  `idx` [N]: one neighbour per Gaussian.  Where the two ellipsoid "surfaces" (utils/ops.py:137-158)
+        do not reach each other along the line of centres, a new Gaussian is put in the gap: centre in the middle of
+        the gap, isotropic scale gap / 6, colour / orientation / opacity copied from the Gaussian itself."""
+        from .knn import distance_to_gaussian_surface
+
+        mean = self.params["mean"].detach()
+        svec, rotmat = self.svec_act, quat_to_rotmat(self.params["qvec"].detach())
+        nn_svec, nn_rotmat, nn_pos = svec[idx], rotmat[idx], mean[idx]
+        nn_surface = distance_to_gaussian_surface(nn_pos, nn_svec, nn_rotmat, mean)
+        surface = distance_to_gaussian_surface(mean, svec, rotmat, nn_pos)
+        dist_to_nn = torch.norm(nn_pos - mean, dim=-1)
+        mask = (surface + nn_surface) < dist_to_nn
+        direction = (nn_pos - mean) / dist_to_nn[..., None]
+        new_mean = (mean + direction * (dist_to_nn + surface - nn_surface)[..., None] / 2.0)[mask]
+        gap = (dist_to_nn - surface - nn_surface)[mask]
+        new = {"mean": new_mean, "qvec": self.params["qvec"].detach()[mask],
+               "svec": torch.log(torch.ones_like(svec[mask]) * gap[..., None] / 6.0)}
+        for name in self._field:  # alpha, color | sh: the raw leaves of the Gaussian itself
+            if name not in new:
+                new[name] = self.params[name].detach()[mask]
+        return new
+
+    def densify_by_compatness(self, K: int = 1) -> int:
+        """:682-694: the K nearest neighbours of every Gaussian (`K_nearest_neighbors(mean, K + 1)`, column 0 = the
+        Gaussian itself dropped), one gap test per neighbour rank, all new Gaussians appended at once."""
+        from .knn import K_nearest_neighbors
+
+        if self.N < 2:
+            return 0
+        _, idx = K_nearest_neighbors(self.params["mean"].detach(), K=K + 1, knn=self._knn())
+        if int(idx.min()) < 0:
+            raise RuntimeError(f"densify_by_compatness: K = {K} neighbours need more than {self.N} Gaussians")
+        parts = [self.densify_by_compatness_with_idx(idx[:, i]) for i in range(K)]
+        new = {name: torch.cat([p[name] for p in parts], dim=0) for name in parts[0]}
+        return self.append(new)
+
+    def densify_by_shrink_then_compatness(self, shrink_factor: float, K: int = 3) -> int:
+        """:741-743: `self.svec = self.svec / shrink_factor` through the activation pair (log of the shrunk scale, as
+        the reference's setter :125-130 stores it), then densify_by_compatness."""
+        raw = self.params["svec"].detach()
+        raw.copy_(torch.log(torch.exp(raw) / shrink_factor))
+        return self.densify_by_compatness(K=K)
+
     def prune(self, radii2d_thresh: float = 0.0, alpha_thresh: float = 0.0, radii3d_thresh: float = 0.0):
         """`prune()` (:1152-1176) with the thresholds already evaluated for the step: by screen radius, then by
         opacity, then by 3-D scale, each on the survivors of the previous one."""
@@ -431,8 +486,12 @@ class GaussianStore:
             n = self.densify_by_split(None, None, get("split_thresh"), 2, get("split_shrink", 0.8),
                                       mask=torch.ones(self.N, dtype=torch.bool, device=self.device),
                                       noise=get("noise"))
+        elif kind == "compatness":  # (:790-797)
+            n = self.densify_by_compatness(K=get("K", 3))
+        elif kind == "shrink_then_compatness":  # (:806-810)
+            n = self.densify_by_shrink_then_compatness(get("surface_shrink", 1.5), K=get("K", 3))
         else:
-            raise NotImplementedError(f"densify type '{kind}' (K-nearest-neighbour variants are not built)")
+            raise NotImplementedError(f"Unknown densify type: {kind}")
         self.reset_densify_info()
         return (n,)
 

@@ -343,6 +343,19 @@ int gsb200_rows_unpack(gsb200_ctx* ctx, float* flat, const float* packed, const 
                        const uint32_t* h_field_width, int32_t n_fields, uint32_t N, const int32_t* idx,
                        uint32_t n_keep, gsb200_stream stream);
 
+/* ================================================================================================
+ * Part 6 -- K nearest neighbours of the Gaussian means (the search behind compactness-based
+ * densification, gs/gaussian_splatting.py:634-743, and the NN / compactness penalties, :1032-1094).  Replaces
+ * utils/ops.py:103-134 `nearest_neighbor` / `K_nearest_neighbors`, i.e. pytorch3d.ops.knn_points(query, mean, K)
+ * (third-party, brute force): for every query the K points with the smallest squared Euclidean distance, ascending,
+ * ties by smaller point index.  points [n_points,3] fp32; queries [n_queries,3] fp32 or NULL = the points query
+ * themselves (every point is then its own first neighbour, distance 0, which the reference drops); idx
+ * [n_queries,K] int64 (-1 where fewer than K points exist), dist2 [n_queries,K] fp32 or NULL (+inf there).
+ * 1 <= K <= 32.  Uniform-grid shell search, exact; everything on `stream`, no synchronisation.
+ * ============================================================================================== */
+int gsb200_knn(gsb200_ctx* ctx, const float* points, uint32_t n_points, const float* queries, uint32_t n_queries,
+               int32_t K, int64_t* idx, float* dist2, gsb200_stream stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -14,6 +14,13 @@ Third-party arithmetic absent from /root/reference: kornia==0.6.0 (requirements.
 from utils/transforms.py:37.  kornia is not installed here and not vendored; `quat_to_rotmat`
 restates its published algorithm (normalise with eps 1e-12, then the standard unit-quaternion
 matrix).  No reference artefact pins that boundary ("parity unpinned" for non-unit quaternions).
+pytorch3d (unpinned, optional import at utils/ops.py:7-14; not installed here, not vendored):
+`pytorch3d.ops.knn_points(p1, p2, K)` behind `nearest_neighbor` / `K_nearest_neighbors` (utils/ops.py:103-134).
+`knn_points` below restates its published contract by brute force (squared Euclidean distance, ascending, int64
+indices); the order of equal distances is not part of that contract and is fixed here to the smaller index.
+No reference artefact pins that boundary either ("parity unpinned" for tie order); everything the reference
+itself computes AROUND the search (distance_to_gaussian_surface, densify_by_compatnes_with_idx, the penalties)
+is pinned by executing its own code over this search (tests/golden/make_compatness_golden.py).
 Everything else is pinned: the torch stages by vectors the reference's OWN functions produced
 (tests/golden/make_pergaussian_golden.py executes project_gaussians / tile_culling_aabb_count /
 CameraInfo unmodified; tests/test_pergaussian_golden_cpu.py), everything downstream of
@@ -489,3 +496,29 @@ def render_view(mean, qvec, svec, alpha, c2w, cam: Cam, *, color=None, sh=None, 
     out["aux"] = dict(mask=mask, mean2d=mean2d, cov2d=cov2d, depth=depth, D=D, ids=ids, start=start, end=end,
                       aabb_tl=tl, aabb_br=br, topleft=topleft, cfg=cfg)
     return out
+
+
+def knn_points(query, points, K: int, return_dist: bool = True):
+    """pytorch3d.ops.knn_points(query, points, K) restated by brute force (see the module docstring): for each query
+    the K points with the smallest squared distance `((p - q)**2).sum(-1)` (fp32), ascending, ties by smaller index.
+    Returns (dist2 [Q,K] fp32, idx [Q,K] int64); `query=None` = the points query themselves.  Slots beyond the number
+    of points hold (+inf, -1).  Same signature as gsgen_b200.knn.knn_points (it is that function's checker)."""
+    pts = points.detach().to(torch.float32).cpu().numpy()
+    q = pts if query is None else query.detach().to(torch.float32).cpu().numpy()
+    n, nq = pts.shape[0], q.shape[0]
+    idx = np.full((nq, K), -1, dtype=np.int64)
+    d2 = np.full((nq, K), np.inf, dtype=np.float32)
+    ar = np.arange(n)
+    for j in range(nq):
+        d = pts - q[j]
+        d = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        if n > 4 * K:  # partial selection first: everything not larger than the K-th smallest value, ties included
+            kth = np.partition(d, K - 1)[K - 1]
+            cand = ar[d <= kth]
+        else:
+            cand = ar
+        order = cand[np.lexsort((cand, d[cand]))][:K]
+        idx[j, : order.shape[0]] = order
+        d2[j, : order.shape[0]] = d[order]
+    dev = points.device
+    return (torch.from_numpy(d2).to(dev) if return_dist else None), torch.from_numpy(idx).to(dev)

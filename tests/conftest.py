@@ -29,7 +29,7 @@ def hostmath():
     d = os.path.join(ROOT, "tests", "hostmath")
     so = os.path.join(d, "libhostmath.so")
     src = os.path.join(d, "hostmath.cpp")
-    hdr = os.path.join(ROOT, "gsgen_b200", "csrc", "gsb200_math.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "gsgen_b200", "csrc", h) for h in ("gsb200_math.cuh", "knn_grid.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++", src, "-o", so])
     return ctypes.CDLL(so)

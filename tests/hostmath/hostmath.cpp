@@ -2,6 +2,10 @@
 // per-Gaussian math the CUDA kernels use) with g++ so the CPU test-suite can check it against the
 // oracle without a GPU.  Never loaded by the product path.
 #include "../../gsgen_b200/csrc/gsb200_math.cuh"
+#include "../../gsgen_b200/csrc/knn_grid.cuh"
+
+#include <algorithm>
+#include <vector>
 
 using namespace gsb;
 
@@ -134,5 +138,57 @@ void hm_adam(long long n, float* p, const float* g, float* m, float* v, double l
 // largest eigenvalue of cov2d as k_preprocess computes it for aux["radii2d"] (gs/gaussian_splatting.py:1240-1245)
 void hm_radius2d(int N, const float* cov2d, float* out) {
   for (int i = 0; i < N; ++i) out[i] = radius2d(cov2d + 4 * i);
+}
+
+// Exact KNN with the SAME grid construction and shell search the device path uses (gsgen_b200/csrc/knn_grid.cuh):
+// bounding box -> knn_make_grid -> cell ids -> stable sort by cell -> cell_start -> knn_query per query.
+// queries == nullptr: the points query themselves (a point is its own first neighbour).  stats[0] = cells,
+// stats[1] = largest number of shells any query visited.
+int hm_knn(int n, const float* pts, int nq, const float* queries, int K, unsigned max_cells, long long* idx,
+           float* d2, int* stats) {
+  if (K < 1 || K > kKnnMaxK) return 1;
+  if (!queries) { queries = pts; nq = n; }
+  float bmin[3] = {INFINITY, INFINITY, INFINITY}, bmax[3] = {-INFINITY, -INFINITY, -INFINITY}, lo[3], hi[3];
+  double sum[3] = {0, 0, 0}, sumsq[3] = {0, 0, 0};
+  for (int i = 0; i < n; ++i)
+    for (int a = 0; a < 3; ++a) {
+      const float v = pts[3 * i + a];
+      bmin[a] = fminf(bmin[a], v); bmax[a] = fmaxf(bmax[a], v);
+      sum[a] += (double)v; sumsq[a] += (double)v * (double)v;
+    }
+  knn_robust_box(bmin, bmax, sum, sumsq, (uint32_t)n, lo, hi);
+  const KnnGrid G = knn_make_grid(lo, hi, (uint32_t)n, max_cells);
+  std::vector<uint32_t> key(n);
+  std::vector<int> perm(n);
+  for (int i = 0; i < n; ++i) { key[i] = knn_cell_id(G, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]); perm[i] = i; }
+  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return key[a] < key[b]; });
+  std::vector<KnnPt> sp(n > 0 ? n : 1);
+  std::vector<uint32_t> skey(n);
+  for (int s = 0; s < n; ++s) {
+    const int i = perm[s];
+    sp[s] = KnnPt{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], i};
+    skey[s] = key[i];
+  }
+  std::vector<int32_t> cell_start(G.cells + 1);
+  for (int c = 0; c <= G.cells; ++c)
+    cell_start[c] = (int32_t)(std::lower_bound(skey.begin(), skey.end(), (uint32_t)c) - skey.begin());
+  int shells = 0;
+  auto run = [&](auto tag) {
+    constexpr int KT = decltype(tag)::value;
+    for (int j = 0; j < nq; ++j) {
+      float bd[KT]; int32_t bi[KT];
+      const int sh = knn_query<KT>(G, sp.data(), cell_start.data(), queries[3 * j], queries[3 * j + 1],
+                                   queries[3 * j + 2], bd, bi);
+      shells = sh > shells ? sh : shells;
+      for (int k = 0; k < K; ++k) { idx[(long long)j * K + k] = bi[k]; d2[(long long)j * K + k] = bd[k]; }
+    }
+  };
+  if (K <= 2) run(std::integral_constant<int, 2>());
+  else if (K <= 4) run(std::integral_constant<int, 4>());
+  else if (K <= 8) run(std::integral_constant<int, 8>());
+  else if (K <= 16) run(std::integral_constant<int, 16>());
+  else run(std::integral_constant<int, 32>());
+  if (stats) { stats[0] = G.cells; stats[1] = shells; }
+  return 0;
 }
 }
