@@ -20,7 +20,7 @@ import torch
 
 from gsgen_b200.scenes import make_scene
 from tests import refpy
-from tests.util import GRAD_RTOL, ROOT, assert_grad_close, classify_image_diff, ocam_of
+from tests.util import GRAD_RTOL, ROOT, assert_grad_close, classify_image_diff, note, ocam_of
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -113,7 +113,7 @@ def test_reference_render_one_runs_unchanged_over_libgsb200(arms, oracle_mod, cf
     t_a = torch.where(ok, grad_a["bg"] / wr, torch.zeros_like(wr))
     t_b = torch.where(ok, grad_b["bg"] / wr, torch.zeros_like(wr))
     classify_image_diff(t_b, t_a, margin, None, atol=1e-4, what=f"render_one {cfg} g_bg / g_rgb (= T)")
-    print(f"\ndrop-in render_one {cfg}: N={sc.N} {W}x{H} N_with_dub={side_a['N_with_dub']} "
+    note(f"drop-in render_one {cfg}: N={sc.N} {W}x{H} N_with_dub={side_a['N_with_dub']} "
           f"max|rgb diff|={report[0]['max_abs_diff']:.2e} flip pixels={n_flip}")
 
 
@@ -157,5 +157,5 @@ def test_reference_sh_forward_runs_unchanged_over_libgsb200(arms, oracle_mod, C,
     for k in ("mean", "qvec", "svec", "sh_coeffs", "alpha"):
         assert_grad_close(grad_b[k], grad_a[k], tol, f"SH C={C} g_{k}")
     assert_grad_close(side_b["mean2d_grad"], side_a["mean2d_grad"], tol, f"SH C={C} g_mean2d")
-    print(f"\ndrop-in SHRenderer.forward C={C} bg={with_bg}: N={sc.N} {W}x{H} N_with_dub={side_a['N_with_dub']} "
+    note(f"drop-in SHRenderer.forward C={C} bg={with_bg}: N={sc.N} {W}x{H} N_with_dub={side_a['N_with_dub']} "
           f"max|rgb diff|={res['max_abs_diff']:.2e} pixels over 1e-4: {n_bad} (all explained)")

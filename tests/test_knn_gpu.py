@@ -9,6 +9,7 @@ import torch
 
 from gsgen_b200.knn import K_nearest_neighbors, knn_points, nearest_neighbor
 from gsgen_b200.store import GaussianStore
+from tests.util import note
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -106,7 +107,7 @@ def test_knn_one_million_points_sampled_check_and_time():
     d2, idx = knn_points(None, pts, 4)
     e1.record()
     torch.cuda.synchronize()
-    print(f"\ngsb200_knn: {n} points, K=4: {e0.elapsed_time(e1):.3f} ms")
+    note(f"gsb200_knn: {n} points (uniform ball), K=4, self query: {e0.elapsed_time(e1):.3f} ms")
     assert torch.equal(idx[:, 0], torch.arange(n, device=DEV)) and float(d2[:, 0].max()) == 0.0
     assert bool((d2[:, 1:] >= d2[:, :-1]).all()) and int(idx.min()) >= 0 and int(idx.max()) < n
     sel = torch.randint(0, n, (512,), generator=g).to(DEV)

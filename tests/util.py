@@ -14,6 +14,16 @@ IMG_ATOL = 1e-4
 GRAD_RTOL = 1e-3
 
 
+def note(line: str):
+    """a measured number a test wants kept (timings, diff statistics): printed, and appended to $GSB200_TEST_NOTES when
+    set (the GPU run scripts point it into gpurun_out/ so the line survives pytest's output capture)"""
+    print("\n" + line)
+    path = os.environ.get("GSB200_TEST_NOTES")
+    if path:
+        with open(path, "a") as f:
+            f.write(line + "\n")
+
+
 def fp(t):
     return ctypes.cast(t.data_ptr(), ctypes.POINTER(ctypes.c_float))
 
