@@ -81,9 +81,11 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--svec-scale", type=float, default=1.0, help="C5 tile-occupancy sweep")
     ap.add_argument("--clock-period", type=float, default=0.1, help="NVML sampling period in s (0 = off)")
-    ap.add_argument("--count-mode", default="sync", choices=["sync", "async"],
-                    help="sync: render_forward waits for N_with_dub (8 bytes); async: no host wait, capacity-sized "
-                         "tile sort (GSB200_OPT_ASYNC_COUNT)")
+    ap.add_argument("--count-mode", default="auto", choices=["auto", "sync", "async"],
+                    help="sync: render_forward waits for N_with_dub (8 bytes) -- the GPU idles whenever the host thread "
+                         "is late (CFS throttling of the container shows up as slow loops); async: no host wait, "
+                         "capacity-sized tile sort (GSB200_OPT_ASYNC_COUNT); auto (default): async at N=1, sync at "
+                         "N>1 (there the sparse all-reduce holds a host wait per step anyway)")
     ap.add_argument("--no-c4-strong", action="store_true", help="skip the C4 strong-scaling sub-record")
     ap.add_argument("--no-ref-ext", action="store_true", help="skip the reference-extension comparison (N=1 only)")
     ap.add_argument("--dense-allreduce", action="store_true",
@@ -382,7 +384,8 @@ class Workload:
             g = torch.Generator().manual_seed(sc.seed + 100 + v)
             self.gouts[v] = torch.randn(self.cams[v].h, self.cams[v].w, 3, generator=g).to(dev)
         self.slot_of = {v: i for i, v in enumerate(self.mine)}  # one library context per in-flight view
-        self.async_count = (args.count_mode == "async")
+        self.count_mode = args.count_mode if args.count_mode != "auto" else ("async" if world == 1 else "sync")
+        self.async_count = (self.count_mode == "async")
         self.last = {}
         self.overflows = 0
 
@@ -873,7 +876,7 @@ def run_ours(args):
                    "grad_allreduce_dense_bytes": vpr.grad_bytes() if world > 1 else 0,
                    "allreduce": dict(vpr.last_allreduce, of=scene.N) if world > 1 else None,
                    "allreduce_buffer": vpr.grad_buffer_kind if world > 1 else None,
-                   "count_mode": args.count_mode,
+                   "count_mode": w.count_mode,
                    "l2": "no explicit flush: inputs larger than L2 -- per step %.0f MB of Gaussian parameters + as many "
                          "gradients + %.0f MB of sort keys/ids stream through the 126 MB L2"
                          % (vpr.grad_bytes() / 1e6, D * 12 / 1e6)},
