@@ -63,15 +63,35 @@ k_knn_stats(uint32_t n, const float* __restrict__ pts, KnnStats* st) {
       ss[a] += __shfl_xor_sync(0xffffffffu, ss[a], o);
     }
   }
+  // block level: the 8 warp results meet in shared memory, one thread per (axis, quantity) folds them and issues the
+  // block's ONE atomic for it (measured round 2 with an atomic per warp: 108 us for 1M points -- 113 k atomics on 12
+  // addresses serialise in L2)
+  __shared__ float s_lo[8][3], s_hi[8][3];
+  __shared__ double s_s[8][3], s_ss[8][3];
+  const int warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      if (lo[a] <= hi[a]) {  // the warp saw at least one non-NaN value on this axis
-        atomicMin(&st->bmin[a], knn_f2ord(lo[a]));
-        atomicMax(&st->bmax[a], knn_f2ord(hi[a]));
-      }
-      atomicAdd(&st->sum[a], s[a]);
-      atomicAdd(&st->sumsq[a], ss[a]);
+    for (int a = 0; a < 3; ++a) { s_lo[warp][a] = lo[a]; s_hi[warp][a] = hi[a]; s_s[warp][a] = s[a]; s_ss[warp][a] = ss[a]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    const int a = threadIdx.x % 3, what = threadIdx.x / 3;  // 0 min, 1 max, 2 sum, 3 sum of squares
+    if (what == 0) {
+      float m = INFINITY;
+      for (int w = 0; w < nwarp; ++w) m = fminf(m, s_lo[w][a]);
+      if (m < INFINITY) atomicMin(&st->bmin[a], knn_f2ord(m));   // (INFINITY: no non-NaN value seen on this axis)
+    } else if (what == 1) {
+      float m = -INFINITY;
+      for (int w = 0; w < nwarp; ++w) m = fmaxf(m, s_hi[w][a]);
+      if (m > -INFINITY) atomicMax(&st->bmax[a], knn_f2ord(m));
+    } else if (what == 2) {
+      double t = 0.0;
+      for (int w = 0; w < nwarp; ++w) t += s_s[w][a];
+      atomicAdd(&st->sum[a], t);
+    } else {
+      double t = 0.0;
+      for (int w = 0; w < nwarp; ++w) t += s_ss[w][a];
+      atomicAdd(&st->sumsq[a], t);
     }
   }
 }
