@@ -94,7 +94,13 @@ class GaussianSplattingRenderer:
         leaves["color"] = color if raw else torch.logit(color)         # inv_activations["sigmoid"]
         leaves["alpha"] = (alpha if raw else torch.logit(alpha)).reshape(-1)
         self.store = GaussianStore(leaves, None, self.device, capacity=capacity, group=group, knn_fn=knn_fn)
-        self.background = background  # None (black), a [3] tensor, or callable(rays_d[H,W,3]) -> [H,W,3]
+        # None (black), a [3] tensor, or callable(rays_d[H,W,3]) -> [H,W,3]; with none given, cfg.background builds the
+        # reference's background module (setup_bg, :207-218; gsgen_b200/backgrounds.py)
+        if background is None and _get(cfg, "background", None) is not None:
+            from .backgrounds import make_background
+
+            background = make_background(_get(cfg, "background")).to(self.device)
+        self.background = background
         self.training = True
         self.step = 0
         self.optimizer = None
@@ -118,9 +124,17 @@ class GaussianSplattingRenderer:
     color = property(lambda self: torch.sigmoid(self.store.params["color"]))
     alpha = property(lambda self: torch.sigmoid(self.store.params["alpha"]))
     rotmat = property(lambda self: quat_to_rotmat(self.store.params["qvec"]))  # :150-152 (kornia quat -> R)
+    principal_axis = rotmat                                                     # :146-148
+    # `cov` is qsvec2rotmat_batched(qvec, svec) in the reference (:154-156, utils/transforms.py:34-46):
+    # `svec.unsqueeze(-2) * R_q`, i.e. the rotation matrix with column j scaled by svec[j] (M = R diag(s)) -- not a
+    # covariance matrix, despite the name
+    cov = property(lambda self: self.svec.unsqueeze(-2) * quat_to_rotmat(self.store.params["qvec"]))
+    bg = property(lambda self: self.background)                                 # the attribute name the reference uses
 
     def train(self, mode: bool = True):
         self.training = mode
+        if isinstance(self.background, torch.nn.Module):  # nn.Module.train() reaches the background in the reference
+            self.background.train(mode)
         return self
 
     def eval(self):
@@ -160,7 +174,7 @@ class GaussianSplattingRenderer:
         if not use_bg or self.background is None:
             return None
         if callable(self.background):
-            return self.background(camera_info.get_rays_d(c2w).to(self.device))
+            return self.background(camera_info.get_rays_d(c2w).to(self.device)).contiguous()
         return self.background.to(self.device).reshape(1, 1, 3).expand(H, W, 3).contiguous()
 
     def render_one(self, c2w, camera_info, use_bg: bool = True, rgb_only: bool = False, return_T: bool = False):
