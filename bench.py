@@ -337,9 +337,11 @@ def run_reference_arm(args):
     H, W = cam.h, cam.w
     t_full = acc_p / args.steps + (acc_c / args.steps) / frac
     val = scene.N * H * W / t_full
+    where = (f"on the FULL image ({px} px)" if frac >= 1.0 else
+             f"on a centred window of {frac:.4g} of the tiles ({px} px), extrapolated by 1/{frac:.4g}")
     sample = (f"each step = all per-Gaussian stages + binning on {scene.N} Gaussians (fwd+bwd) + SH composite fwd+bwd "
-              f"on a centred window of {frac:.4g} of the tiles ({px} px); measured {dt:.3f} s/step of which "
-              f"{acc_c / args.steps:.3f} s composite; value = N*H*W / (t_per_gaussian + t_composite/{frac:.4g})")
+              f"{where}; measured {dt:.3f} s/step of which {acc_c / args.steps:.3f} s composite; "
+              f"value = N*H*W / (t_per_gaussian + t_composite/{frac:.4g})")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "weak",
