@@ -396,6 +396,49 @@ class GaussianStore:
         self.reset_densify_info()
         return n_clone, n_split
 
+    # ---- the legacy rule (gs/gaussian_splatting.py:820-946; `use_legacy: True` in conf/base.yaml, corgi.yaml, ...) ----
+    def densify_legacy(self, mean2d_thresh: float, split_thresh: float, split_shrink: float = 0.8, noise=None):
+        """`densify_legacy`: ONE selection `accum / (cnt + 1e-5) > mean2d_thresh`, split where any scale exceeds
+        `split_thresh` (two children, scale / split_shrink / 2), clone elsewhere.  Result order as the reference builds
+        it: the rows that are not split (clone sources included), the clones, the children (all first halves, then all
+        second halves -- `repeat(2, 1)`).  The reference then RE-CREATES the optimizer (`set_optimizer(opt_cfg, step)`,
+        :938): every Adam moment is dropped and the step counter restarts -- reproduced by zeroing both moment buffers
+        and the optimizer's update count.  Returns (num_split, num_clone)."""
+        mask = self.mean_2d_grad_accum / (self.cnt + 1e-5) > mean2d_thresh
+        svec = self.svec_act
+        split_mask = torch.logical_and(mask, (svec > split_thresh).any(dim=-1))
+        clone_mask = torch.logical_and(mask, torch.logical_not(split_mask))
+        n_split, n_clone = int(torch.count_nonzero(split_mask)), int(torch.count_nonzero(clone_mask))
+        n_old = self.N
+        rep = lambda t: t.detach()[split_mask].repeat(2, *([1] * (t.dim() - 1)))
+        split_mean, split_qvec, split_svec = rep(self.params["mean"]), rep(self.params["qvec"]), svec[split_mask].repeat(2, 1)
+        if noise is None:
+            noise = torch.randn(n_split * 2, 3, device=self.device)  # (:859) -- replicas must draw the SAME numbers
+            if self.world_size() > 1:
+                src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+                dist.broadcast(noise, src=src, group=self.group)
+        elif callable(noise):
+            noise = noise(n_split * 2)
+        if noise.shape[0] != n_split * 2:
+            raise RuntimeError(f"split noise has {noise.shape[0]} rows, {n_split * 2} are needed")
+        rot_t = quat_to_rotmat(split_qvec).transpose(-1, -2)
+        children = {"mean": split_mean + torch.einsum("bij,bj->bi", rot_t, noise.to(self.device) * split_svec),
+                    "qvec": split_qvec, "svec": torch.log(split_svec / split_shrink / 2.0)}
+        clones = {}
+        for name in self._field:
+            clones[name] = self.params[name].detach()[clone_mask]
+            if name not in children:
+                children[name] = rep(self.params[name])
+        self.append(clones)
+        self.append(children)
+        pad = torch.zeros(self.N - n_old, dtype=torch.bool, device=self.device)
+        self.prune_by_mask(torch.cat((split_mask, pad)))
+        for buf in (self.exp_avg, self.exp_avg_sq):  # the re-created optimizer starts without state
+            buf.zero_()
+        if self.optimizer is not None:
+            self.optimizer.n_steps = 0
+        return n_split, n_clone
+
     # ---- compactness-based densification (gs/gaussian_splatting.py:634-743) ----------------------------------
     def _knn(self):
         if self.knn_fn is not None:
@@ -462,19 +505,28 @@ class GaussianStore:
 
     # ---- the trainer-facing dispatchers (step gating as the reference) -------------------------------------
     def densify_step(self, step: int, cfg) -> Optional[tuple]:
-        """`densify(step)` (gs/gaussian_splatting.py:751-817) for the non-legacy types this store implements: runs when
+        """`densify(step)` (gs/gaussian_splatting.py:751-817), legacy and non-legacy branches: runs when
         `cfg.enabled`, `warm_up <= step <= end` and `step % period == 0` (step_check(..., run_at_zero=True)); resets
         the accumulators afterwards (:816-817).  cfg: mapping with the keys of conf/renderer/*.yaml `densify:`.
         Returns the counts of the operation that ran, or None."""
         from .renderer import step_check
 
         get = cfg.get if hasattr(cfg, "get") else (lambda k, d=None: getattr(cfg, k, d))
-        if not get("enabled", False) or get("use_legacy", False):
+        if not get("enabled", False):
             return None
         if step < get("warm_up") or step > get("end") or not step_check(step, get("period"), True):
             return None
         self.sync_densify_info()  # view-parallel replicas: the selection below must see the whole batch's statistics
         kind = get("type", "official")
+        if get("use_legacy", False):  # (:759-768): the legacy rule, then -- by substring of the type -- a compactness pass
+            res = self.densify_legacy(get("mean2d_thresh"), get("split_thresh"), get("split_shrink", 0.8),
+                                      noise=get("noise"))
+            if "shrink_then_compatness" in kind:
+                res = res + (self.densify_by_shrink_then_compatness(get("surface_shrink", 1.5), K=get("K", 3)),)
+            elif "compatness" in kind:
+                res = res + (self.densify_by_compatness(K=get("K", 3)),)
+            self.reset_densify_info()
+            return res
         if kind == "official":
             res = self.densify_official(get("mean2d_thresh"), get("split_thresh"), get("n_splits", 2),
                                         get("split_shrink", 0.8), noise=get("noise"))
