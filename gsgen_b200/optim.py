@@ -54,6 +54,28 @@ def no_decay(tot_steps, lr_start, lr_end, warmup_steps=0) -> Callable[[int], flo
 lr_schedulers = dict(nothing=no_decay, cosine=cosine_decay, exp=exp_decay)
 
 
+class CompanionAdam:
+    """torch.optim.Adam for the few parameters that live outside the Gaussian arena -- the background module's, which
+    the reference puts into the SAME optimizer as param group "bg" with its own scheduler
+    (gs/gaussian_splatting.py:383-419, conf/base.yaml:26 `lr.bg`).  Driven by FlatAdam.step / zero_grad through
+    `FlatAdam.companions`; the schedule is evaluated at the trainer's step like every other group's (:451-454)."""
+
+    def __init__(self, params, lr: LrSpec, max_steps: int = 15000, betas=(0.9, 0.999), eps: float = 1e-15):
+        self.params = [p for p in params]
+        self.scheduler = make_scheduler(lr, max_steps)
+        self.opt = torch.optim.Adam(self.params, lr=float(self.scheduler(0)), betas=betas, eps=eps)
+
+    def step(self, train_step: int):
+        lr = float(self.scheduler(train_step))
+        for g in self.opt.param_groups:
+            g["lr"] = lr
+        self.opt.step()
+        return lr
+
+    def zero_grad(self):
+        self.opt.zero_grad()
+
+
 def make_scheduler(spec: LrSpec, max_steps: int) -> Callable[[int], float]:
     """A config entry -> scheduler, as gs/gaussian_splatting.py:268-292 reads `cfg.lr.<field>`:
     a number is a constant lr; `[start, end, steps, type]` (conf/base.yaml:13-22) selects a schedule."""
@@ -121,6 +143,8 @@ class FlatAdam:
 
     def zero_grad(self):
         self.flat_grad.zero_()
+        for c in getattr(self, "companions", ()):  # parameters outside the arena (the background module's)
+            c.zero_grad()
 
     def step(self, train_step: int = None, grad_scale: float = 1.0):
         """One Adam update.  `train_step` is the trainer's step counter the schedules are evaluated at (defaults to
@@ -140,4 +164,6 @@ class FlatAdam:
             ctypes.c_uint64(self.flat_param.numel()), self._fields, ctypes.c_int32(len(self.layout)),
             ctypes.c_double(self.betas[0]), ctypes.c_double(self.betas[1]), ctypes.c_double(self.eps),
             ctypes.c_int64(self.n_steps), ctypes.c_float(grad_scale), _lib.stream_ptr(dev)))
+        for c in getattr(self, "companions", ()):  # the reference's Adam also holds a "bg" param group (:383-396)
+            c.step(train_step)
         return lrs

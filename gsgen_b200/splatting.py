@@ -142,7 +142,8 @@ class GaussianSplattingRenderer:
 
     # ---- optimizer -----------------------------------------------------------------------------------------
     def setup_lr(self, lr_cfg):
-        """cfg.lr (conf/base.yaml:12-26): field -> number | [start, end, steps, type]"""
+        """cfg.lr (conf/base.yaml:12-26): field -> number | [start, end, steps, type]; `bg` is the background's group"""
+        self._bg_lr = _get(lr_cfg, "bg")
         self._lr_cfg = {f: _get(lr_cfg, f) for f in FIELDS}
         missing = [f for f, v in self._lr_cfg.items() if v is None]
         if missing:
@@ -158,6 +159,18 @@ class GaussianSplattingRenderer:
         self.optimizer = self.store.make_optimizer(self._lr_cfg, max_steps=_get(opt_cfg, "max_steps", 15000),
                                                    betas=tuple(_get(args, "betas", (0.9, 0.999))),
                                                    eps=float(_get(args, "eps", 1e-8)))
+        # the background's parameters are param group "bg" of the same Adam in the reference (:383-396); here they are
+        # the only parameters outside the arena and ride along as a companion of the flat optimizer
+        bg_params = [p for p in self.background.parameters()] if isinstance(self.background, torch.nn.Module) else []
+        if bg_params:
+            if getattr(self, "_bg_lr", None) is None:
+                raise RuntimeError("no learning rate for 'bg' (cfg.lr.bg, conf/base.yaml:26): the background module "
+                                   "has parameters")
+            from .optim import CompanionAdam
+
+            self.optimizer.companions = [CompanionAdam(
+                bg_params, self._bg_lr, max_steps=_get(opt_cfg, "max_steps", 15000),
+                betas=tuple(_get(args, "betas", (0.9, 0.999))), eps=float(_get(args, "eps", 1e-8)))]
         self.optimizer.train_step = step
         self.store.zero_grad()
         return self.optimizer
@@ -221,6 +234,15 @@ class GaussianSplattingRenderer:
 
     def prune(self, step: int):
         return self.store.prune_step(step, _get(self.cfg, "prune", {"enabled": False}))
+
+    # called directly by the trainer's up-sampling fine-tune stage (trainer.py:799-801)
+    def densify_by_compatness(self, K: int = 1) -> int:
+        """:682-694"""
+        return self.store.densify_by_compatness(K=K)
+
+    def reset_densify_info(self):
+        """:476-479"""
+        self.store.reset_densify_info()
 
     # ---- auxiliary losses (gs/gaussian_splatting.py:950-1122) ----------------------------------------------
     def _penalty_cfg(self, key):

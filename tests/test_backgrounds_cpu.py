@@ -89,3 +89,50 @@ def test_renderer_builds_its_background_from_cfg(oracle_mod):
     # no cfg.background and no argument: black (None), as before
     r2 = GaussianSplattingRenderer({}, init, device="cpu", render_fn=lambda *a, **k: None)
     assert r2.bg is None
+
+
+def test_background_parameters_are_optimised_with_the_renderer(oracle_mod):
+    """the reference's Adam holds a "bg" param group with its own schedule (gs/gaussian_splatting.py:383-419,
+    conf/base.yaml:26): a FIXED background's colour is a parameter and trains (conf/renderer/regular.yaml)"""
+    from gsgen_b200.optim import CompanionAdam
+    from gsgen_b200.splatting import GaussianSplattingRenderer
+
+    g = torch.Generator().manual_seed(0)
+    N = 30
+    init = {"mean": torch.randn(N, 3, generator=g), "qvec": torch.randn(N, 4, generator=g),
+            "svec": torch.rand(N, 3, generator=g) * 0.1 + 0.01, "color": torch.rand(N, 3, generator=g) * 0.8 + 0.1,
+            "alpha": torch.rand(N, generator=g) * 0.8 + 0.1}
+    cfg = {"background": {"type": "fixed", "color": [0.2, 0.3, 0.4], "device": "cpu", "random_aug": False,
+                          "random_aug_prob": 0.0}}
+    r = GaussianSplattingRenderer(cfg, init, device="cpu", render_fn=lambda *a, **k: None)
+    lr = {"mean": 1e-3, "qvec": 1e-3, "svec": 1e-3, "color": 1e-2, "alpha": 1e-2}
+    r.setup_lr(lr)
+    with pytest.raises(RuntimeError, match="bg"):
+        r.set_optimizer({"type": "Adam", "opt_args": {"eps": 1e-15}})
+    r.setup_lr(dict(lr, bg=[0.003, 0.0003, 100, "exp"]))
+    opt = r.set_optimizer({"type": "Adam", "opt_args": {"eps": 1e-15}})
+    (comp,) = opt.companions
+    assert isinstance(comp, CompanionAdam) and comp.params[0] is r.bg.bg_color
+    # one update of the companion = torch.optim.Adam on a twin parameter with the scheduled lr
+    w = torch.randn(4, 5, 3, generator=g)
+    twin = torch.nn.Parameter(r.bg.bg_color.detach().clone())
+    ref = torch.optim.Adam([twin], lr=0.0, eps=1e-15)
+    for step in (0, 50):
+        for p_, bgimg in ((r.bg.bg_color, r.bg(torch.zeros(4, 5, 3))), (twin, twin.reshape(1, 1, 3).expand(4, 5, 3))):
+            p_.grad = None
+            (bgimg * w).sum().backward()
+        used = comp.step(step)
+        ref.param_groups[0]["lr"] = float(comp.scheduler(step))
+        ref.step()
+        assert used == pytest.approx(float(comp.scheduler(step))) and torch.equal(r.bg.bg_color.detach(), twin.detach())
+    assert comp.scheduler(0) == pytest.approx(0.003) and comp.scheduler(100) == pytest.approx(0.0003, rel=1e-6)
+    opt.flat_grad.fill_(1.0)
+    opt.zero_grad()  # FlatAdam.zero_grad reaches the companion
+    assert r.bg.bg_color.grad is None or float(r.bg.bg_color.grad.abs().max()) == 0.0
+    assert float(opt.flat_grad.abs().max()) == 0.0
+    # a background without parameters needs no lr
+    r2 = GaussianSplattingRenderer({"background": {"type": "random", "device": "cpu"}}, init, device="cpu",
+                                   render_fn=lambda *a, **k: None)
+    r2.setup_lr(lr)
+    assert not getattr(r2.set_optimizer({"type": "Adam", "opt_args": {"eps": 1e-15}}), "companions", [])
+

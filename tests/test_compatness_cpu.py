@@ -248,6 +248,18 @@ def test_compat_penalty_matches_reference(oracle_mod, kind):
     assert torch.allclose(total.detach(), loss.detach()) and "auxiliary/total" in w.scalars
 
 
+def test_trainer_level_compatness_calls(oracle_mod):
+    """trainer.py:799-801 calls renderer.densify_by_compatness(3) and renderer.reset_densify_info() directly"""
+    g = _load()
+    r = _renderer(g, oracle_mod, {})
+    n0 = r.N
+    r.store.cnt += 1.0
+    n_new = r.densify_by_compatness(3)
+    assert n_new == int(g["s1_num"]) and r.N == n0 + n_new and r.mean.shape[0] == r.N
+    r.reset_densify_info()
+    assert r.store.cnt.shape[0] == r.N and float(r.store.cnt.abs().max()) == 0.0
+
+
 def test_nn_penalty_matches_reference(oracle_mod):
     g = _load()
     r = _renderer(g, oracle_mod, {"NN": {"value": 0.3}})

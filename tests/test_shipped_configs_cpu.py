@@ -63,7 +63,7 @@ def test_shipped_renderer_config_drives_the_renderer(oracle_mod, rel, sub):
                                   knn_fn=oracle_mod.knn_points)
     if "background" in cfg:
         assert r.bg is not None
-    r.setup_lr({"mean": 1e-3, "qvec": 1e-3, "svec": 1e-3, "color": 1e-2, "alpha": 1e-2})
+    r.setup_lr({"mean": 1e-3, "qvec": 1e-3, "svec": 1e-3, "color": 1e-2, "alpha": 1e-2, "bg": 3e-3})
     r.set_optimizer({"type": "Adam", "opt_args": {"eps": 1e-15}})
     cam, c2w = sc.cams[0], sc.c2ws[0]
     dens, prune = cfg.get("densify", {}), cfg.get("prune", {})
