@@ -404,8 +404,48 @@ class GaussianSplattingRenderer:
 
     @classmethod
     def load(cls, cfg, ckpt, device="cuda", **kw) -> "GaussianSplattingRenderer":
+        """`load(cfg, ckpt)` (:312-339): a path or dict; a renderer-only checkpoint (the params incl. its own `cfg`) or a
+        trainer checkpoint (`{"params", "cfg": {... "renderer": ...}}`).  The configuration stored in the checkpoint is
+        the base, `cfg` (may be None, as in vis.py:17) overrides it key by key; the background's state is restored when
+        it fits (the reference only prints a message when it does not)."""
         if not isinstance(ckpt, dict):
             ckpt = torch.load(ckpt, map_location="cpu")
+        stored = ckpt.get("cfg") or {}
         if "params" in ckpt:
+            stored = _get(stored, "renderer", None) or {}
             ckpt = ckpt["params"]
-        return cls(cfg, dict({k: ckpt[k] for k in FIELDS}, raw=True), device, **kw)
+            stored = _get(ckpt, "cfg", None) or stored  # (our get_params_for_save keeps the renderer cfg with the params)
+        merged = dict(stored.items()) if hasattr(stored, "items") else {}
+        if cfg is not None:
+            merged.update(dict(cfg.items()) if hasattr(cfg, "items") else vars(cfg))
+        r = cls(merged, dict({k: ckpt[k] for k in FIELDS}, raw=True), device, **kw)
+        bg_state = ckpt.get("bg") if hasattr(ckpt, "get") else None
+        if bg_state and isinstance(r.background, torch.nn.Module):
+            try:
+                r.background.load_state_dict(bg_state)
+            except Exception:  # "the background will be randomly initialized" (:333-337)
+                pass
+        return r
+
+    def to(self, device) -> "GaussianSplattingRenderer":
+        """nn.Module.to as vis.py:17 uses it (`load(None, ckpt).to("cuda")`): the arena moves to `device` (parameters,
+        gradients, Adam moments, statistics); an optimizer has to be set again afterwards, as after a fresh load"""
+        device = torch.device(device)
+        if device.type == self.device.type and (device.index is None or device.index == self.device.index):
+            return self
+        old = self.store
+        names = list(old._field)
+        new = GaussianStore({n: old.params[n].detach() for n in names}, old.C, device, capacity=old.cap, group=old.group,
+                            knn_fn=old.knn_fn)
+        for src, dst in zip(old._buffers()[1:], new._buffers()[1:]):
+            for n in names:
+                new._rows(dst, n, new.N).copy_(old._rows(src, n, old.N))
+        for a in ("mean_2d_grad_accum", "cnt", "max_radii2d"):
+            setattr(new, a, getattr(old, a).to(device))
+        self.store, self.device, self.optimizer = new, device, None
+        if isinstance(self.background, torch.nn.Module):
+            self.background.to(device)
+        elif torch.is_tensor(self.background):
+            self.background = self.background.to(device)
+        self._pending = []
+        return self

@@ -136,3 +136,33 @@ def test_background_parameters_are_optimised_with_the_renderer(oracle_mod):
     r2.setup_lr(lr)
     assert not getattr(r2.set_optimizer({"type": "Adam", "opt_args": {"eps": 1e-15}}), "companions", [])
 
+
+def test_checkpoint_round_trip_restores_cfg_and_background(tmp_path):
+    """vis.py:17 `GaussianSplattingRenderer.load(None, ckpt).to("cuda")`: the configuration and the background state
+    come out of the checkpoint (gs/gaussian_splatting.py:312-339)"""
+    from gsgen_b200.splatting import GaussianSplattingRenderer
+
+    g = torch.Generator().manual_seed(3)
+    N = 25
+    init = {"mean": torch.randn(N, 3, generator=g), "qvec": torch.randn(N, 4, generator=g),
+            "svec": torch.rand(N, 3, generator=g) * 0.1 + 0.01, "color": torch.rand(N, 3, generator=g) * 0.8 + 0.1,
+            "alpha": torch.rand(N, generator=g) * 0.8 + 0.1}
+    cfg = {"T_thresh": 2e-4, "background": {"type": "fixed", "color": [0.2, 0.3, 0.4], "device": "cpu",
+                                            "random_aug": False, "random_aug_prob": 0.0}}
+    r = GaussianSplattingRenderer(cfg, init, device="cpu", render_fn=lambda *a, **k: None)
+    with torch.no_grad():
+        r.bg.bg_color.copy_(torch.tensor([0.9, 0.8, 0.7]))  # a trained background colour
+    fake = lambda *a, **k: None
+    # renderer-only checkpoint
+    p1 = str(tmp_path / "renderer.pt")
+    torch.save(r.get_params_for_save(), p1)
+    a = GaussianSplattingRenderer.load(None, p1, device="cpu", render_fn=fake)
+    # trainer checkpoint (params + the experiment cfg with its `renderer` block)
+    p2 = str(tmp_path / "trainer.pt")
+    torch.save({"params": r.get_params_for_save(), "cfg": {"renderer": cfg, "max_steps": 10}, "step": 5}, p2)
+    b = GaussianSplattingRenderer.load({"T_thresh": 1e-4}, p2, device="cpu", render_fn=fake)
+    for x in (a, b):
+        assert x.N == N and torch.equal(x.mean.detach(), r.mean.detach())
+        assert isinstance(x.bg, B.FixedBackground) and torch.equal(x.bg.bg_color.detach(), torch.tensor([0.9, 0.8, 0.7]))
+    assert a.cfg["T_thresh"] == 2e-4 and b.cfg["T_thresh"] == 1e-4  # the argument overrides the stored value
+    assert a.to("cpu") is a  # same device: nothing moves
