@@ -457,6 +457,21 @@ def warm_up(args, step, world, dev):
     torch.cuda.synchronize()
 
 
+def roofline_extras(C, n_visible, d_eff, tiles, H, W, traffic, launch_ms, peak_gbs):
+    """The two numbers SURVEY.md §8(d) wants NEXT to the contract-definition `achieved`: (ii) the compulsory lower bound
+    of the forward composite -- every visible Gaussian's record + payload once, the consumed ids, tile ranges, outputs --
+    and (i) the DRAM-side fraction: measured dram__bytes (one ncu launch, `traffic`) / launch time / HBM peak."""
+    K = 3 * C * C
+    compulsory = n_visible * 4 * (7 + K) + 4 * d_eff + 8 * tiles + 16 * H * W
+    out = {"compulsory_bytes": float(compulsory),
+           "compulsory_formula": "N_visible*4*(7+3C^2) + 4*D_eff + 8*tiles + 16*H*W (SURVEY.md §8(d)-ii)",
+           "compulsory_frac": (compulsory / 1e9) / (launch_ms / 1e3) / peak_gbs if launch_ms > 0 else None}
+    if traffic and launch_ms > 0:
+        out["dram_gbs"] = (traffic / 1e9) / (launch_ms / 1e3)
+        out["dram_frac"] = out["dram_gbs"] / peak_gbs
+    return out
+
+
 def allreduce_bytes(vpr):
     """bytes the step's gradient collective(s) carried (sparse: the union's rows + the 1-byte-per-Gaussian mask)"""
     la = vpr.last_allreduce
@@ -799,6 +814,10 @@ def run_ours(args):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu.get("composite_fwd_dram_bytes"),
                 "peak_source": peak_src, "alg_bytes_per_launch": ab["composite_fwd"], "avg_launch_ms": fwd_ms,
                 "alg_bytes_formula": "D_eff*(4+4*(7+3C^2)) + 8*tiles + 16*H*W (SURVEY.md §8(d))"}
+    try:  # (never at the price of the bench line)
+        roofline.update(roofline_extras(C, N_vis, D_eff, th * tw, H, W, roofline["traffic"], fwd_ms, peak))
+    except Exception as ex:
+        roofline["extras_error"] = repr(ex)
 
     # ---- end to end through the public API with host buffers (pinned): per step H2D of the step's inputs
     # (camera pose + upstream gradient image) and D2H of the rendered image

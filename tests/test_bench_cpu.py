@@ -133,3 +133,15 @@ def test_reference_arm_sets_its_thread_count(monkeypatch):
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     got, want = out.stdout.split()[-2:]
     assert got == want, out.stdout + out.stderr
+
+
+def test_roofline_extras_compulsory_bytes_and_dram_fraction():
+    """the compulsory lower bound and the DRAM-side fraction next to the contract-definition number"""
+    import bench
+
+    r = bench.roofline_extras(4, 1_000_000, 686_820.0, 4096, 1024, 1024, 65_536_000.0, 0.379, 6564.2)
+    assert r["compulsory_bytes"] == 1_000_000 * 4 * 55 + 4 * 686_820 + 8 * 4096 + 16 * 1024 * 1024
+    assert abs(r["dram_gbs"] - 65.536 / 0.379) < 1e-6 and abs(r["dram_frac"] - r["dram_gbs"] / 6564.2) < 1e-12
+    assert 0 < r["compulsory_frac"] < 1
+    r = bench.roofline_extras(4, 10, 5.0, 4, 32, 32, None, 0.0, 6564.2)  # no capture / no time: no division
+    assert "dram_frac" not in r and r["compulsory_frac"] is None
