@@ -472,6 +472,30 @@ def roofline_extras(C, n_visible, d_eff, tiles, H, W, traffic, launch_ms, peak_g
     return out
 
 
+def dominant_kernel_roofline(stages, alg_bytes, ncu, peak_gbs, sm_mhz):
+    """The same accounting for the kernel that dominates the step (the composite backward: 57 % of it) as `roofline`
+    gives for the kernel north_star names (the composite forward): algorithmic bytes / measured launch time / HBM peak,
+    the DRAM-side fraction from the committed ncu capture, and the limiter that is actually active -- instruction issue
+    and the shared-memory data pipe."""
+    name = max(stages, key=lambda k: stages[k]["ms"])
+    ms = stages[name]["ms"]
+    out = {"kernel": {"composite_bwd": "k_composite_bwd_sh<C=4,fused>", "composite_fwd": "k_composite_fwd<SH,C=4>"}.get(name, name),
+           "stage": name, "share_of_stage_sum": ms / sum(v["ms"] for v in stages.values()), "bound": "hbm",
+           "achieved": stages[name]["alg_gbs"], "peak": peak_gbs, "unit": "GB/s",
+           "frac": stages[name]["alg_gbs"] / peak_gbs if stages[name]["alg_gbs"] else None,
+           "alg_bytes_per_launch": alg_bytes.get(name), "avg_launch_ms": ms,
+           "traffic": ncu.get(f"{name}_dram_bytes")}
+    if out["traffic"] and ms > 0:
+        out["dram_frac"] = (out["traffic"] / 1e9) / (ms / 1e3) / peak_gbs
+    inst = ncu.get(f"{name}_warp_inst")
+    if inst and ms > 0:
+        t_issue = inst / (148 * 4 * sm_mhz * 1e6) * 1e3
+        out["issue_roofline"] = {"warp_instructions": inst, "min_ms_at_full_issue": t_issue, "frac": t_issue / ms}
+    if ncu.get(f"{name}_smem_wavefront_pct") is not None:
+        out["smem_data_pipe_pct_in_capture"] = ncu[f"{name}_smem_wavefront_pct"]
+    return out
+
+
 def allreduce_bytes(vpr):
     """bytes the step's gradient collective(s) carried (sparse: the union's rows + the 1-byte-per-Gaussian mask)"""
     la = vpr.last_allreduce
@@ -871,6 +895,10 @@ def run_ours(args):
                  "frac": t_issue / fwd_ms if fwd_ms > 0 else None,
                  "source": ncu.get("source", "profiles/traffic.json")}
     roofline["issue_roofline"] = issue
+    try:  # (never at the price of the bench line)
+        roofline["dominant_kernel"] = dominant_kernel_roofline(stages, ab, ncu, peak, sm_mhz)
+    except Exception as ex:
+        roofline["dominant_kernel"] = {"error": repr(ex)}
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
         try:

@@ -145,3 +145,24 @@ def test_roofline_extras_compulsory_bytes_and_dram_fraction():
     assert 0 < r["compulsory_frac"] < 1
     r = bench.roofline_extras(4, 10, 5.0, 4, 32, 32, None, 0.0, 6564.2)  # no capture / no time: no division
     assert "dram_frac" not in r and r["compulsory_frac"] is None
+
+
+def test_dominant_kernel_roofline_from_a_committed_bench_line():
+    """fed with the stages of the last committed bench line and profiles/traffic.json"""
+    import json
+    import os
+
+    import bench
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    line = json.loads(open(os.path.join(root, "profiles", "r2_bench_c3_default_final2_async.json")).read())
+    ncu = bench.ncu_numbers("c3")
+    ab = {k: v["alg_gbs"] * 1e9 * v["ms"] / 1e3 for k, v in line["stages"].items()}
+    r = bench.dominant_kernel_roofline(line["stages"], ab, ncu, 6564.2, 1965.0)
+    assert r["stage"] == "composite_bwd" and 0.5 < r["share_of_stage_sum"] < 0.65
+    assert abs(r["frac"] - line["stages"]["composite_bwd"]["frac_of_hbm_peak"]) < 1e-9
+    assert 0.5 < r["issue_roofline"]["frac"] < 0.6 and 0.015 < r["dram_frac"] < 0.02
+    assert r["smem_data_pipe_pct_in_capture"] == 73.5
+    # no capture: still a record
+    r2 = bench.dominant_kernel_roofline(line["stages"], ab, {}, 6564.2, 1965.0)
+    assert r2["traffic"] is None and "issue_roofline" not in r2
