@@ -21,6 +21,9 @@ Row movers: on a CUDA device the two hand-written kernels of csrc/store.cu (`gsb
 launch that moves all fields of all four buffers into the arena's shadow buffers, which are then swapped in;
 `gsb200_store_append`: one launch).  On CPU tensors (the test-suite exercises this host logic without a GPU) the same
 row operations are torch indexing ops; `tests/test_store_gpu.py` checks the kernels against that path bit for bit.
+Rules built on those row operations: clone / split / "official" / "scale" / "all" (:551-632, :770-810), the legacy rule the
+top-level experiment configs select (`densify_legacy`, :820-946, incl. its optimizer reset), compactness-based
+densification over the K-nearest-neighbour kernel (:634-743; csrc/knn.cu) and the three prune rules (:1124-1176).
 Selection rules follow the reference bit for bit, including two quirks that a drop-in must keep:
   * `densify_by_clone` compares `torch.norm(grads, dim=-1)` of the 1-D per-Gaussian statistic, i.e. ONE number for the
     whole scene, with the threshold (:616-618);
