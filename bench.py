@@ -365,7 +365,7 @@ def workload_name(wl, scene, cam):
 class Workload:
     """One synthetic scene + its views, replicated parameters, this rank's shard of the views."""
 
-    def __init__(self, args, wl, world, rank, dev):
+    def __init__(self, args, wl, world, rank, dev, count_mode=None):
         from gsgen_b200.parallel import ViewParallelRenderer, shard_views
         from gsgen_b200.rasterizer import render_view
         from gsgen_b200.scenes import make_scene
@@ -386,7 +386,8 @@ class Workload:
             g = torch.Generator().manual_seed(sc.seed + 100 + v)
             self.gouts[v] = torch.randn(self.cams[v].h, self.cams[v].w, 3, generator=g).to(dev)
         self.slot_of = {v: i for i, v in enumerate(self.mine)}  # one library context per in-flight view
-        self.count_mode = args.count_mode if args.count_mode != "auto" else ("async" if world == 1 else "sync")
+        self.count_mode = count_mode or (args.count_mode if args.count_mode != "auto"
+                                         else ("async" if world == 1 else "sync"))
         self.async_count = (self.count_mode == "async")
         self.last = {}
         self.overflows = 0
@@ -858,7 +859,10 @@ def run_ours(args):
     c4 = None
     if wl == "c3" and not args.no_c4_strong and args.svec_scale == 1.0:
         try:
-            w4 = Workload(args, "c4", world, rank, dev)
+            # the SAME count mode at every N, so that ms(N=1) / ms(N) compares like with like (`auto` would time N = 1
+            # asynchronously and N > 1 synchronously); with 8 views per step the host wait is diluted anyway
+            w4 = Workload(args, "c4", world, rank, dev,
+                          count_mode=("sync" if args.count_mode == "auto" else args.count_mode))
             for _ in range(5):
                 w4.step()
             torch.cuda.synchronize()
@@ -866,7 +870,8 @@ def run_ours(args):
             ms4 = sorted(x[0] for x in r4)[N_LOOPS // 2]
             cam4 = w4.cams[0]
             c4 = {"workload": workload_name("c4", w4.scene, cam4), "scaling": "strong", "views_per_step": 8,
-                  "views_per_gpu": len(w4.mine), "ms_per_step": ms4, "ms_per_step_all_runs": [x[0] for x in r4],
+                  "views_per_gpu": len(w4.mine), "count_mode": w4.count_mode, "ms_per_step": ms4,
+                  "ms_per_step_all_runs": [x[0] for x in r4],
                   "value": 8 * w4.scene.N * cam4.h * cam4.w / (ms4 / 1e3), "unit": UNIT,
                   "grad_allreduce_bytes": allreduce_bytes(w4.vpr) if world > 1 else 0,
                   "allreduce": dict(w4.vpr.last_allreduce, of=w4.scene.N) if world > 1 else None,
