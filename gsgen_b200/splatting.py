@@ -190,16 +190,29 @@ class GaussianSplattingRenderer:
             return self.background(camera_info.get_rays_d(c2w).to(self.device)).contiguous()
         return self.background.to(self.device).reshape(1, 1, 3).expand(H, W, 3).contiguous()
 
-    def render_one(self, c2w, camera_info, use_bg: bool = True, rgb_only: bool = False, return_T: bool = False):
+    def render_one(self, c2w, camera_info, use_bg: bool = True, rgb_only: bool = False, overrides=None,
+                   return_T: bool = False):
+        """render_one (:1198-1421), same positional order.  `overrides`: {field: ACTIVATED tensor} replacing
+        `self.<field>` for this view (get_with_overrides :1179-1183; utils/relight.py:64 re-colours a scene with it) --
+        the view then runs on activated values (`raw_params=False`), gradients flow to the leaves through torch's own
+        exp / sigmoid and to the override tensors directly."""
         p = self.store.params
+        leaves, raw = (p["mean"], p["qvec"], p["svec"], p["alpha"], p["color"]), True
+        if overrides:
+            unknown = [k for k in overrides if k not in FIELDS]
+            if unknown:
+                raise RuntimeError(f"overrides for unknown fields {unknown}")
+            act = {f: (overrides[f] if f in overrides else getattr(self, f)) for f in FIELDS}
+            leaves, raw = (act["mean"], act["qvec"], act["svec"], act["alpha"], act["color"]), False
         out = self._render_fn(
-            p["mean"], p["qvec"], p["svec"], p["alpha"], c2w, camera_info, color=p["color"],
-            bg=self._bg_image(camera_info, c2w, use_bg), rgb_only=rgb_only, raw_params=True,
+            leaves[0], leaves[1], leaves[2], leaves[3], c2w, camera_info, color=leaves[4],
+            bg=self._bg_image(camera_info, c2w, use_bg), rgb_only=rgb_only, raw_params=raw,
             frustum_radius=_get(self.cfg, "frustum_culling_radius", 6.0),
             tile_radius=_get(self.cfg, "tile_culling_radius", 6.0), T_thresh=_get(self.cfg, "T_thresh", 1e-4),
             skip_frustum_culling=_get(self.cfg, "skip_frustum_culling", False),
             depth_detach=_get(self.cfg, "depth_detach", True),
-            grad_sink=self.store.grad_views if self.training else None,
+            # (the flat gradient sink holds gradients w.r.t. the RAW leaves: only the raw-leaf path may write into it)
+            grad_sink=self.store.grad_views if (self.training and raw) else None,
             # one library context per in-flight view: the views of a batch are all rendered before ONE loss.backward()
             # (trainer.py:575-599), and a context keeps a view's binning + splat records until its backward has run
             slot=len(self._pending) if self.training else 0)

@@ -208,3 +208,39 @@ def test_auxiliary_losses_match_the_reference_methods(gold, oracle_mod):
     w.add_histogram = lambda k, v, step=None: w.h.__setitem__(k, len(v))
     r.log(w, 3)
     assert "renderer/num_gaussians" in w.s and "renderer/alpha/grad_max" in w.s and "hists/max_radii2d" in w.h
+
+
+def test_render_one_overrides_recolour_a_view(gold, oracle_mod):
+    """render_one(..., overrides={"color": activated}) (gs/gaussian_splatting.py:1179-1183, utils/relight.py:64): the
+    view equals the one of a renderer whose colour leaf IS that colour, gradients reach the override tensor and -- for
+    the fields that were not overridden -- the arena"""
+    def fn(mean, qvec, svec, alpha, c2w, cam, color=None, bg=None, rgb_only=False, raw_params=False, grad_sink=None,
+           slot=0, frustum_radius=6.0, tile_radius=6.0, T_thresh=1e-4, skip_frustum_culling=False, depth_detach=True):
+        s, a, c = (torch.exp(svec), torch.sigmoid(alpha), torch.sigmoid(color)) if raw_params else (svec, alpha, color)
+        out = oracle_mod.render_view(mean, qvec, s, a, c2w, ocam_of(cam), color=c, bg=bg, rgb_only=rgb_only,
+                                     depth_detach=depth_detach, frustum_radius=frustum_radius, tile_radius=tile_radius,
+                                     thresh=T_thresh)
+        au = out["aux"]
+        out["aux"] = _Aux(mask=au["mask"], mean2d_masked=au["mean2d"], radii2d=torch.zeros(mean.shape[0]),
+                          N_with_dub=au["D"])
+        out.setdefault("T", None)
+        return out
+
+    init = {k: gold[f"a_in_{k}"] for k in ("mean", "qvec", "svec", "color", "alpha")}
+    fx, fy, cx, cy, w, h, near, far = gold["a_cam"].tolist()
+    cam = CameraInfo(fx, fy, cx, cy, int(w), int(h), near, far)
+    c2w = gold["a_c2w"]
+    g = torch.Generator().manual_seed(9)
+    new_color = (torch.rand(init["color"].shape, generator=g) * 0.9 + 0.05).requires_grad_()
+    r = GaussianSplattingRenderer({}, init, device="cpu", render_fn=fn)
+    r.store.zero_grad()
+    img = r.render_one(c2w, cam, use_bg=False, rgb_only=True, overrides={"color": new_color})["rgb"]
+    r2 = GaussianSplattingRenderer({}, dict(init, color=new_color.detach()), device="cpu", render_fn=fn)
+    ref = r2.render_one(c2w, cam, use_bg=False, rgb_only=True)["rgb"]
+    assert torch.allclose(img, ref, atol=2e-6) and float((img - r.render_one(c2w, cam, use_bg=False, rgb_only=True)["rgb"]).abs().max()) > 1e-3
+    img.sum().backward()
+    assert new_color.grad is not None and float(new_color.grad.abs().max()) > 0
+    assert float(r.store.grad_views["mean"].abs().max()) > 0  # not overridden: gradient lands in the arena
+    assert float(r.store.grad_views["color"].abs().max()) == 0  # overridden: the colour leaf took no part
+    with pytest.raises(RuntimeError):
+        r.render_one(c2w, cam, overrides={"sh": new_color})
