@@ -41,6 +41,32 @@ class CameraInfo:
         fy = cy / np.tan(fov / 2)
         return cls(fx, fy, cx, cy, W, H, near_plane, far_plane)
 
+    # ---- resolution changes the trainer applies to its cameras (utils/camera.py:230-258; trainer.py:786-787 calls
+    # cam_info.set_reso(reso) for the up-sampling stage) ----------------------------------------------------------
+    def _refresh(self):
+        self.yfov = 2 * np.arctan(self.h / (2 * self.fy))
+        self.aspect = self.w / self.h
+
+    def downsample(self, scale):
+        self.fx /= scale; self.fy /= scale; self.cx /= scale; self.cy /= scale
+        self.w //= scale; self.h //= scale
+        self._refresh()
+
+    def upsample(self, scale):
+        """(the reference refreshes neither yfov nor aspect here; both are invariant under a uniform integer scale)"""
+        self.fx *= scale; self.fy *= scale; self.cx *= scale; self.cy *= scale
+        self.w *= int(scale); self.h *= int(scale)
+
+    def set_reso(self, reso: int):
+        self.fx = self.fy = reso
+        self.cx = self.cy = reso / 2.0
+        self.w = self.h = reso
+        self._refresh()
+
+    def get_camera_intrinsic(self, device="cuda"):
+        """utils/camera.py:361-368"""
+        return torch.tensor([[self.fx, 0, self.cx], [0, self.fy, self.cy], [0, 0, 1]]).to(device)
+
     def get_frustum(self, c2w: torch.Tensor):
         """-> (normals[6,3], pts[6,3]) fp32 on c2w's device; reference utils/camera.py:260-294."""
         up = -c2w[:, 1]

@@ -93,3 +93,34 @@ def test_viewer_camera_helpers():
         want = ns2["from_fov_camera"](lambda *a: a, fov, aspect, reso, 0.01, 100.0)
         got = CameraInfo.from_fov_camera(fov, aspect, reso, 0.01, 100.0)
         assert (got.fx, got.fy, got.cx, got.cy, got.w, got.h, got.near_plane, got.far_plane) == want
+
+
+def test_camera_info_resolution_changes_and_intrinsics():
+    """CameraInfo.downsample / upsample / set_reso / get_camera_intrinsic / from_fov_camera against the reference's own
+    class (utils/camera.py:219-368), attribute for attribute"""
+    import torch.nn.functional as F
+
+    from gsgen_b200.camera import CameraInfo
+
+    tree = ast.parse(open(os.path.join(REF, "utils/camera.py")).read())
+    node = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "CameraInfo")
+    ns = {"np": np, "torch": torch, "F": F, "console": None}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), "utils/camera.py", "exec"), ns)
+    Ref = ns["CameraInfo"]
+
+    def same(a, b):
+        for k in ("fx", "fy", "cx", "cy", "w", "h", "yfov", "aspect", "near_plane", "far_plane"):
+            assert float(getattr(a, k)) == pytest.approx(float(getattr(b, k)), rel=1e-12), k
+
+    for args in ((400.0, 410.0, 256.0, 250.0, 512, 500, 0.01, 100.0), (128.0, 128.0, 64.0, 64.0, 128, 128, 0.1, 10.0)):
+        a, b = CameraInfo(*args), Ref(*args)
+        same(a, b)
+        for op, arg in (("downsample", 2), ("upsample", 2), ("set_reso", 96), ("upsample", 3), ("downsample", 4)):
+            getattr(a, op)(arg); getattr(b, op)(arg)
+            same(a, b)
+        assert torch.equal(a.get_camera_intrinsic("cpu"), b.get_camera_intrinsic("cpu"))
+    a, b = CameraInfo.from_fov_camera(0.9, 1.5, 300, 0.01, 100.0), Ref.from_fov_camera(0.9, 1.5, 300, 0.01, 100.0)
+    same(a, b)
+    a, b = CameraInfo.from_reso(64), Ref.from_reso(64)
+    for k in ("fx", "fy", "cx", "cy", "w", "h"):  # (the reference's from_reso hard-codes near 0.01 / far 1000)
+        assert float(getattr(a, k)) == float(getattr(b, k))
