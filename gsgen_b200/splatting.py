@@ -131,6 +131,12 @@ class GaussianSplattingRenderer:
     cov = property(lambda self: self.svec.unsqueeze(-2) * quat_to_rotmat(self.store.params["qvec"]))
     bg = property(lambda self: self.background)                                 # the attribute name the reference uses
 
+    @property
+    def is_densifying(self) -> bool:
+        """:163-169"""
+        d = _get(self.cfg, "densify", None)
+        return bool(d is not None and _get(d, "enabled", False) and _get(d, "warm_up", 0) < self.step < _get(d, "end", 0))
+
     def train(self, mode: bool = True):
         self.training = mode
         if isinstance(self.background, torch.nn.Module):  # nn.Module.train() reaches the background in the reference
@@ -217,6 +223,10 @@ class GaussianSplattingRenderer:
             # (trainer.py:575-599), and a context keeps a view's binning + splat records until its backward has run
             slot=len(self._pending) if self.training else 0)
         aux = out["aux"]
+        try:  # `self.total_dub_gaussians = N_with_dub` (:1264); -1 while unresolved in the asynchronous count mode
+            self.total_dub_gaussians = int(aux["N_with_dub"])
+        except (KeyError, TypeError, ValueError):
+            self.total_dub_gaussians = None
         if self.training:
             self._pending.append(aux)  # mask + mean2d gradient are read in post_backward (:1246-1250)
         res = {"rgb": out["rgb"]}
@@ -377,6 +387,8 @@ class GaussianSplattingRenderer:
         """scalars / histograms the reference writes: parameter bounds, gradient bounds, learning rates, densification
         statistics.  `writer`: anything with add_scalar / add_histogram (tensorboard SummaryWriter)."""
         _scalar(writer, "renderer/num_gaussians", self.N, step)
+        if getattr(self, "total_dub_gaussians", None) is not None:  # (:1493-1495) N_with_dub of the last rendered view
+            _scalar(writer, "renderer/n_gaussians_with_dub", self.total_dub_gaussians, step)
         st = self.store
         for field in FIELDS:
             v = getattr(self, field)
@@ -389,6 +401,8 @@ class GaussianSplattingRenderer:
         if self.optimizer is not None:
             for name, lr in self.optimizer.lr_at(self.step).items():
                 _scalar(writer, f"lr/{name}", lr, step)
+            for c in getattr(self.optimizer, "companions", ()):  # the "bg" param group (:1551-1558)
+                _scalar(writer, "lr/bg", float(c.scheduler(self.step)), step)
         if hasattr(writer, "add_histogram"):
             writer.add_histogram("hists/mean", self.mean.norm(dim=-1).cpu().numpy(), step)
             writer.add_histogram("hists/svec_min", self.svec.min(dim=-1)[0].cpu().numpy(), step)
@@ -396,7 +410,7 @@ class GaussianSplattingRenderer:
             writer.add_histogram("hists/alpha", self.alpha.cpu().numpy(), step)
             writer.add_histogram("hists/grad_mean", st.grad_views["mean"].norm(dim=-1).cpu().numpy(), step)
             writer.add_histogram("hists/max_radii2d", st.max_radii2d.cpu().numpy(), step)
-            if _get(_get(self.cfg, "densify", {}), "enabled", False):
+            if self.is_densifying:  # (:1486-1487)
                 writer.add_histogram("hists/grad_mean2d", st.mean_2d_grad_accum.cpu().numpy(), step)
                 writer.add_histogram("hists/cnt", st.cnt.cpu().numpy(), step)
 

@@ -208,6 +208,18 @@ def test_auxiliary_losses_match_the_reference_methods(gold, oracle_mod):
     w.add_histogram = lambda k, v, step=None: w.h.__setitem__(k, len(v))
     r.log(w, 3)
     assert "renderer/num_gaussians" in w.s and "renderer/alpha/grad_max" in w.s and "hists/max_radii2d" in w.h
+    # the tag set of the reference's log / log_bounds / log_grad_bounds / log_statistics (:1477-1549) for one rendered view
+    r.render_one(gold["a_c2w"], cam, rgb_only=True)
+    assert r.total_dub_gaussians == int(gold["a_N_with_dub"])
+    w2 = W()
+    w2.h = {}
+    w2.add_histogram = lambda k, v, step=None: w2.h.__setitem__(k, len(v))
+    r.log(w2, 3)
+    want = {"renderer/num_gaussians", "renderer/n_gaussians_with_dub"} | {
+        f"renderer/{f}/{k}" for f in ("mean", "qvec", "svec", "color", "alpha") for k in ("min", "max", "mean", "grad_min", "grad_max")}
+    assert want <= set(w2.s), want - set(w2.s)
+    assert {"hists/mean", "hists/svec_min", "hists/svec_max", "hists/alpha", "hists/grad_mean", "hists/max_radii2d"} <= set(w2.h)
+    assert not r.is_densifying and "hists/cnt" not in w2.h  # no densify block in this cfg (:163-169, :1486-1487)
 
 
 def test_render_one_overrides_recolour_a_view(gold, oracle_mod):
